@@ -1,0 +1,95 @@
+"""ctypes binding of libtimegan_b200.so (C ABI declared in include/timegan_b200.h).
+
+There is NO fallback: if the shared library is missing the import fails loudly, and every compute entry
+point needs a CUDA device (SURVEY.md section 8b "Must NOT exist: ... CPU fallback").
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libtimegan_b200.so"
+
+# flags (keep in sync with include/timegan_b200.h)
+GRU_SAVE, GRU_NO_BULK, GRU_DY_LAST = 1, 2, 4
+PROJ_FP32, PROJ_BF16 = 0, 1
+
+if not LIB_PATH.exists():
+    raise ImportError(
+        f"{LIB_PATH} not found: build the CUDA extension first "
+        f"(`python -c 'import __graft_entry__ as g; g.build()'` or eeg-gan-timegan-cgan_b200/csrc/build.sh). "
+        "There is no CPU/PyTorch fallback for the TimeGAN hot path.")
+
+lib = C.CDLL(str(LIB_PATH))
+
+_vp, _i, _ll, _ull, _f, _sz = C.c_void_p, C.c_int, C.c_longlong, C.c_ulonglong, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes).  Every symbol of include/timegan_b200.h must be listed (tests check this).
+SIGNATURES = {
+    "tg_version": (_i, []),
+    "tg_last_error": (C.c_char_p, []),
+    "tg_device_sm_count": (_i, []),
+    "tg_proj": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "tg_dgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i]),
+    "tg_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
+    "tg_wgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz]),
+    "tg_gru_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "tg_gru_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "tg_gru_jvp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "tg_gru_jvp_bwd": (_i, [_vp] * 14 + [_i, _i, _i, _i]),
+    "tg_reduce_workspace_bytes": (_sz, []),
+    "tg_sqdiff_sum": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _sz]),
+    "tg_scaled_diff": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i]),
+    "tg_diff1_sum": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz]),
+    "tg_diff1_grad": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "tg_center_scale": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i]),
+    "tg_colsum_workspace_bytes": (_sz, [_i]),
+    "tg_colsum": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _sz]),
+    "tg_acf_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "tg_acf_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "tg_acf_bwd_final": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i]),
+    "tg_sumsq_workspace_bytes": (_sz, [_i, C.POINTER(_ll)]),
+    "tg_sumsq": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_ll), _vp, _vp, _sz]),
+    "tg_adam": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _vp,
+                     _f, _f, _f, _f, _f, _i, _f]),
+    "tg_rng_uniform": (_i, [_vp, _vp, _ll, _ull, _ull, _f, _f]),
+    "tg_rng_add_normal": (_i, [_vp, _vp, _vp, _ll, _f, _ull, _ull]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = library older than the header: rebuild
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+ABI_VERSION = lib.tg_version()
+
+
+def last_error() -> str:
+    return (lib.tg_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        kind = "argument error" if rc < 0 else "CUDA error"
+        raise RuntimeError(f"libtimegan_b200 {what}: {kind} {rc}: {last_error()}")
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(t: torch.Tensor, name: str = "tensor") -> torch.Tensor:
+    """The hot path has no CPU implementation: refuse anything that is not a CUDA fp32 tensor."""
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"timegan_b200: {name} is on {t.device}; the TimeGAN hot path only exists as sm_100a CUDA kernels "
+            "(no CPU fallback). Move the model and data to a CUDA device.")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"timegan_b200: {name} must be float32, got {t.dtype}")
+    return t
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,148 @@
+// extern "C" surface of libtimegan_b200.so (see include/timegan_b200.h). Thin forwarding + error plumbing.
+#include "../../include/timegan_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+#include "losses.h"
+#include <mutex>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void tg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int tg_check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    tg_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+int tg_num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      sms = n;
+    else
+      return 148;  // B200; do not cache a failed query
+  }
+  return sms;
+}
+
+size_t tg_sumsq_ws_bytes(int n, const long long* sizes);
+
+extern "C" {
+
+int tg_version(void) { return TG_ABI_VERSION; }
+const char* tg_last_error(void) { return g_err; }
+int tg_device_sm_count(void) { return tg_num_sms(); }
+
+int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+            int M, int N, int K, int accumulate, int mode) {
+  if (mode == TG_PROJ_BF16) {
+    int rc = tg_proj_tc_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
+    if (rc != TG_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core tile cannot take run exact fp32
+  }
+  return tg_gemm_nt_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
+}
+
+int tg_dgrad(void* stream, const float* dG, int ldg, const float* W, int ldw, float* dX, int ldx, int M, int N, int K,
+             int accumulate) {
+  return tg_gemm_nn_impl((cudaStream_t)stream, dG, ldg, W, ldw, dX, ldx, M, N, K, accumulate);
+}
+
+size_t tg_wgrad_workspace_bytes(int M, int N, int K) { return tg_wgrad_ws_bytes(M, N, K); }
+
+int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
+             int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes) {
+  return tg_wgrad_impl((cudaStream_t)stream, dG, ldg, A, lda, dW, lddw, db, M, N, K, a_shift_T, accumulate, (float*)ws,
+                       ws_bytes);
+}
+
+int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, float* y, float* q, int B, int T, int H,
+               int flags) {
+  return tg_gru_fwd_impl((cudaStream_t)stream, gi, w_hh, b_hh, y, q, B, T, H, flags);
+}
+
+int tg_gru_bwd(void* stream, const float* dy, const float* rzn, const float* q, const float* y, const float* w_hh,
+               float* dgi, float* dq, int B, int T, int H, int flags) {
+  return tg_gru_bwd_impl((cudaStream_t)stream, dy, rzn, q, y, w_hh, dgi, dq, B, T, H, flags);
+}
+
+int tg_gru_jvp_fwd(void* stream, float* gid, const float* rzn, const float* q, const float* y, const float* w_hh,
+                   float* ydot, float* qdot, int B, int T, int H, int flags) {
+  return tg_gru_jvp_fwd_impl((cudaStream_t)stream, gid, rzn, q, y, w_hh, ydot, qdot, B, T, H, flags);
+}
+
+int tg_gru_jvp_bwd(void* stream, const float* hbar, const float* hdbar, const float* rzn, const float* q,
+                   const float* ta, const float* qdot, const float* y, const float* ydot, const float* w_hh,
+                   float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags) {
+  return tg_gru_jvp_bwd_impl((cudaStream_t)stream, hbar, hdbar, rzn, q, ta, qdot, y, ydot, w_hh, gib, qb, gidb, qdb, B,
+                             T, H, flags);
+}
+
+size_t tg_reduce_workspace_bytes(void) { return tg_reduce_ws_bytes(); }
+int tg_sqdiff_sum(void* stream, const float* a, const float* b, long long n, float* out, void* ws, size_t ws_bytes) {
+  return tg_sqdiff_sum_impl((cudaStream_t)stream, a, b, n, out, ws, ws_bytes);
+}
+int tg_scaled_diff(void* stream, const float* a, const float* b, const float* coef, float* out, long long n,
+                   int accumulate) {
+  return tg_scaled_diff_impl((cudaStream_t)stream, a, b, coef, out, n, accumulate);
+}
+int tg_diff1_sum(void* stream, const float* h, int B, int T, int H, float* out, void* ws, size_t ws_bytes) {
+  return tg_diff1_sum_impl((cudaStream_t)stream, h, B, T, H, out, ws, ws_bytes);
+}
+int tg_diff1_grad(void* stream, const float* h, const float* coef, float* out, int B, int T, int H, int accumulate) {
+  return tg_diff1_grad_impl((cudaStream_t)stream, h, coef, out, B, T, H, accumulate);
+}
+int tg_center_scale(void* stream, const float* x, const float* mean, const float* scale, float* out, long long rows,
+                    int C) {
+  return tg_center_scale_impl((cudaStream_t)stream, x, mean, scale, out, rows, C);
+}
+int tg_acf_fwd(void* stream, const float* xz, int B, int T, int C, int L, float* part) {
+  return tg_acf_fwd_impl((cudaStream_t)stream, xz, B, T, C, L, part);
+}
+int tg_acf_bwd(void* stream, const float* xz, const float* S, int B, int T, int C, int L, float* gz, float* stat) {
+  return tg_acf_bwd_impl((cudaStream_t)stream, xz, S, B, T, C, L, gz, stat);
+}
+int tg_acf_bwd_final(void* stream, const float* gz, const float* xz, const float* mean_gz, const float* kc,
+                     const float* inv_s, float* dx, long long rows, int C, int accumulate) {
+  return tg_acf_bwd_final_impl((cudaStream_t)stream, gz, xz, mean_gz, kc, inv_s, dx, rows, C, accumulate);
+}
+
+size_t tg_colsum_workspace_bytes(int N) { return tg_colsum_ws_bytes(N); }
+int tg_colsum(void* stream, const float* X, int ld, int M, int N, float* out, int accumulate, void* ws,
+              size_t ws_bytes) {
+  return tg_colsum_impl((cudaStream_t)stream, X, ld, M, N, out, accumulate, (float*)ws, ws_bytes);
+}
+
+size_t tg_sumsq_workspace_bytes(int n, const long long* sizes) { return tg_sumsq_ws_bytes(n, sizes); }
+int tg_sumsq(void* stream, int n, const float* const* grads, const long long* sizes, float* out_sumsq, void* ws,
+             size_t ws_bytes) {
+  return tg_sumsq_multi_impl((cudaStream_t)stream, n, grads, sizes, out_sumsq, ws, ws_bytes);
+}
+int tg_adam(void* stream, int n, float* const* params, const float* const* grads, float* const* exp_avg,
+            float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr, float beta1,
+            float beta2, float eps, int step, float grad_scale) {
+  return tg_adam_multi_impl((cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, sizes, sumsq, max_norm, lr,
+                            beta1, beta2, eps, step, grad_scale);
+}
+
+int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,
+                   float hi) {
+  return tg_rng_uniform_impl((cudaStream_t)stream, out, n, seed, offset, lo, hi);
+}
+int tg_rng_add_normal(void* stream, const float* in, float* out, long long n, float std, unsigned long long seed,
+                      unsigned long long offset) {
+  return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, std, seed, offset);
+}
+
+}  // extern "C"

@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# Builds libtimegan_b200.so for sm_100a next to the Python host package (in-tree, travels with gpurun).
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+OUT="$HERE/../libtimegan_b200.so"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall -Xptxas -v
+       --expt-relaxed-constexpr -I"$HERE" -I"$HERE/../../include")
+SRCS=(api gru_fwd gru_bwd gru_jvp gemm_ffma proj_tcgen05 losses optim rng)
+mkdir -p "$HERE/build"
+pids=()
+for s in "${SRCS[@]}"; do
+  if [[ ! -f "$HERE/build/$s.o" || "$HERE/$s.cu" -nt "$HERE/build/$s.o" || -n "$(find "$HERE" -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer "$HERE/build/$s.o" 2>/dev/null)" ]]; then
+    ( "$NVCC" "${FLAGS[@]}" -c "$HERE/$s.cu" -o "$HERE/build/$s.o" > "$HERE/build/$s.log" 2>&1 || { cat "$HERE/build/$s.log"; exit 1; } ) &
+    pids+=($!)
+  fi
+done
+for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
+"$NVCC" -shared -o "$OUT" $(printf "$HERE/build/%s.o " "${SRCS[@]}") -lcudart_static -ldl -lrt -lpthread
+echo "built $OUT"

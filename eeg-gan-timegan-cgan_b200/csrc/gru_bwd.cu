@@ -1,0 +1,182 @@
+// Persistent BPTT kernel for one GRU layer on sm_100a (north_star kernel (2)).
+//
+// Replaces autograd's backward of the per-timestep nn.GRU loop (loss.backward() at
+// timeGAN/train_timegan.py:140,159,219,267 and the dX-only pass inside autograd.grad, tt:200) --
+// math of SURVEY.md Appendix A.2.
+//
+// Mirror image of gru_fwd.cu: one CTA owns BT sequences for all T steps (t = T-1 .. 0), W_hh^T lives in
+// registers (thread (k,q) holds column k of W_hh for the row-slice q of each gate), the carried dh lives
+// in the registers of the lane that owns hidden unit k, the per-step dGH vector is exchanged through a
+// double-buffered shared-memory vector (one __syncthreads per step), saved r,z,n / q / h_{t-1} and dy
+// stream in through the bulk-async ring and dGI = [dar,daz,dan] / dq = dan*r stream out in place.
+// The weight-gradient contractions (K = B*T) and dX = dGI W_ih are separate GEMM kernels.
+#include "chunk_pipe.cuh"
+#include "kernels.h"
+
+namespace {
+
+struct BwdParams {
+  const float* dy;   // (B,T,H), or (B,H) when dy_last
+  const float* rzn;  // (B,T,3H) saved r,z,n
+  const float* q;    // (B,T,H)  saved q
+  const float* y;    // (B,T,H)  layer output (h_t); h_{t-1} is read with a -1 row shift
+  const float* whh;  // (3H,H)
+  float* dgi;        // (B,T,3H) out
+  float* dq;         // (B,T,H)  out: dGH_n
+  int B, T, H;
+  int dy_last;
+  int bulk;
+};
+
+template <int HP, int G, int BT, int TC, int NST>
+__global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel(BwdParams p) {
+  constexpr int KS = HP / G;
+  static_assert(KS % 4 == 0, "slice must be float4 granular");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int k = tid / G, ql = tid % G;
+  const int H = p.H, T = p.T;
+  const int b0 = blockIdx.x * BT;
+  const int nb = min(BT, p.B - b0);
+
+  float* dgs = reinterpret_cast<float*>(smem_raw);                     // [2][BT][3][HP]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dgs + 2 * BT * 3 * HP);
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * 3 * HP * 4 + NST * 8 + 127) / 128) * 128);
+
+  ChunkPipe<4, BT, TC, NST> pipe;
+  pipe.g[0] = const_cast<float*>(p.rzn); pipe.gst[0] = p.dgi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | TG_STRM_STORE; pipe.shift[0] = 0;
+  pipe.g[1] = const_cast<float*>(p.q);   pipe.gst[1] = p.dq;  pipe.w[1] = H;     pipe.mode[1] = TG_STRM_LOAD | TG_STRM_STORE; pipe.shift[1] = 0;
+  pipe.g[2] = const_cast<float*>(p.dy);  pipe.gst[2] = nullptr; pipe.w[2] = H;   pipe.mode[2] = p.dy_last ? 0 : TG_STRM_LOAD;  pipe.shift[2] = 0;
+  pipe.g[3] = const_cast<float*>(p.y);   pipe.gst[3] = nullptr; pipe.w[3] = H;   pipe.mode[3] = TG_STRM_LOAD;                  pipe.shift[3] = -1;
+  pipe.layout();
+  pipe.stages = stages; pipe.full = bars;
+  pipe.T = T; pipe.nb = nb; pipe.b0 = b0; pipe.NC = (T + TC - 1) / TC;
+  pipe.reverse = true; pipe.bulk = p.bulk != 0;
+
+  // W_hh^T slice: wt[g][m] = W_hh[g*H + jj][k], jj = (i*G+ql)*4+c
+  float wt[3][KS];
+#pragma unroll
+  for (int g = 0; g < 3; ++g)
+#pragma unroll
+    for (int i = 0; i < KS / 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int jj = (i * G + ql) * 4 + c;
+        wt[g][4 * i + c] = (k < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + k] : 0.f;
+      }
+  for (int i = tid; i < 2 * BT * 3 * HP; i += HP * G) dgs[i] = 0.f;
+  float carry[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) carry[b] = 0.f;
+  pipe.start();
+  __syncthreads();
+
+  int par = 0;
+  for (int c = 0; c < pipe.NC; ++c) {
+    pipe.acquire(c);
+    const int s = c % NST;
+    const int t0 = pipe.t0_of(c);
+    const int tcn = pipe.tcn_of(c);
+    for (int tl = tcn - 1; tl >= 0; --tl) {
+      const int t = t0 + tl;
+      float* dg = dgs + par * BT * 3 * HP;
+      float cz[BT];
+      // ---- pointwise gate derivatives for hidden unit k (lane b % G of the group handles sequence b) ----
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        cz[b] = 0.f;
+        if (ql == (b % G) && k < H && b < nb) {
+          float* gp = pipe.row(s, 0, b, tl);
+          float* qp = pipe.row(s, 1, b, tl);
+          const float r = gp[k], z = gp[H + k], n = gp[2 * H + k], qv = qp[k];
+          const float hp = (t > 0) ? pipe.row(s, 3, b, tl)[k] : 0.f;
+          float dyv;
+          if (p.dy_last) dyv = (t == T - 1) ? p.dy[(size_t)(b0 + b) * H + k] : 0.f;
+          else dyv = pipe.row(s, 2, b, tl)[k];
+          const float dh = dyv + carry[b];
+          const float dn = dh * (1.f - z);
+          const float dz = dh * (hp - n);
+          const float dan = dn * (1.f - n * n);
+          const float daz = dz * z * (1.f - z);
+          const float dar = dan * qv * r * (1.f - r);
+          const float dqv = dan * r;
+          cz[b] = dh * z;
+          gp[k] = dar; gp[H + k] = daz; gp[2 * H + k] = dan; qp[k] = dqv;
+          dg[(b * 3 + 0) * HP + k] = dar;
+          dg[(b * 3 + 1) * HP + k] = daz;
+          dg[(b * 3 + 2) * HP + k] = dqv;
+        }
+      }
+      if (tl == 0 && pipe.bulk) fence_async_smem();
+      __syncthreads();
+      // ---- carry_k = dh*z + sum_rows dGH[row] * W_hh[row][k] ----
+      float acc[BT];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+#pragma unroll
+      for (int g = 0; g < 3; ++g)
+#pragma unroll
+        for (int i = 0; i < KS / 4; ++i)
+#pragma unroll
+          for (int b = 0; b < BT; ++b) {
+            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 3 + g) * HP)[i * G + ql];
+            acc[b] = fmaf(wt[g][4 * i + 0], dv.x, acc[b]);
+            acc[b] = fmaf(wt[g][4 * i + 1], dv.y, acc[b]);
+            acc[b] = fmaf(wt[g][4 * i + 2], dv.z, acc[b]);
+            acc[b] = fmaf(wt[g][4 * i + 3], dv.w, acc[b]);
+          }
+#pragma unroll
+      for (int b = 0; b < BT; ++b) carry[b] = cz[b] + group_sum<G>(acc[b]);
+      par ^= 1;
+    }
+    // the closing barrier of the chunk: all in-place writes of this stage happened before the last
+    // step's __syncthreads above, so the stage can be handed to the store engine now
+    pipe.release(c);
+  }
+  pipe.drain();
+}
+
+template <int HP, int G, int BT, int TC, int NST>
+int launch_bwd(cudaStream_t st, const BwdParams& p) {
+  const int widths[4] = {3 * p.H, p.H, p.H, p.H};
+  size_t smem = ((2 * BT * 3 * HP * 4 + NST * 8 + 127) / 128) * 128 +
+                (size_t)NST * ChunkPipe<4, BT, TC, NST>::stage_floats_for(widths) * 4;
+  auto kern = gru_bwd_kernel<HP, G, BT, TC, NST>;
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { tg_set_error("gru_bwd: smem attr %zu B: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    configured = smem;
+  }
+  dim3 grid((p.B + BT - 1) / BT), block(HP * G);
+  kern<<<grid, block, smem, st>>>(p);
+  return tg_check_launch("gru_bwd");
+}
+
+template <int HP, int G>
+int dispatch_bt(cudaStream_t st, const BwdParams& p, int bt) {
+  constexpr int TC = (HP >= 128) ? 4 : 8, NST = 3;
+  switch (bt) {
+    case 1: return launch_bwd<HP, G, 1, TC, NST>(st, p);
+    case 2: return launch_bwd<HP, G, 2, TC, NST>(st, p);
+    case 4: return launch_bwd<HP, G, 4, TC, NST>(st, p);
+  }
+  tg_set_error("gru_bwd: bad BT %d", bt);
+  return TG_ERR_ARG;
+}
+
+}  // namespace
+
+int tg_gru_bwd_impl(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y,
+                    const float* whh, float* dgi, float* dq, int B, int T, int H, int flags) {
+  TG_REQUIRE(dy && rzn && q && y && whh && dgi && dq, TG_ERR_ARG, "gru_bwd: null pointer");
+  TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_bwd: bad shape B=%d T=%d H=%d", B, T, H);
+  TG_REQUIRE(H <= 128, TG_ERR_UNSUPPORTED, "gru_bwd: hidden size %d > 128 needs the cluster kernel (not built yet)", H);
+  BwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, H, (flags & TG_GRU_DY_LAST) ? 1 : 0, 0};
+  p.bulk = (H % 4 == 0) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(y) && tg_aligned16(dgi) &&
+           tg_aligned16(dq) && (p.dy_last || tg_aligned16(dy)) && !(flags & TG_GRU_NO_BULK);
+  const int bto = (flags >> 8) & 0xff;
+  if (H <= 32) return dispatch_bt<32, 4>(st, p, tg_pick_bt(B, 32, bto));
+  if (H <= 64) return dispatch_bt<64, 4>(st, p, tg_pick_bt(B, 64, bto));
+  return dispatch_bt<128, 4>(st, p, tg_pick_bt(B, 128, bto));
+}

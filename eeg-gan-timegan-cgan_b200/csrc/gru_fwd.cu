@@ -1,0 +1,178 @@
+// Persistent fused GRU layer forward for sm_100a (north_star kernel (1)).
+//
+// Replaces the per-timestep loop inside torch.nn.GRU reached from timeGAN/timegan_model.py:32-34
+// (GRUStack.forward) -- math of SURVEY.md Appendix A.1, gate order r,z,n, h0 = 0.
+//
+// One CTA owns BT whole sequences for all T steps.  W_hh lives in registers (thread (j,q) holds the
+// three gate rows of hidden unit j for the k-slice q), h_{t-1} lives in a double-buffered shared-memory
+// vector, the pre-computed input projection gi (B,T,3H) streams in through a bulk-async (TMA) ring and
+// r,z,n / q / y stream out the same way (r,z,n overwrite gi in place, in smem and in HBM).
+// Exactly one __syncthreads per timestep.
+#include "chunk_pipe.cuh"
+#include "kernels.h"
+
+namespace {
+
+struct FwdParams {
+  float* gi;         // (B,T,3H) in: x W_ih^T + b_ih ; out (if save): r,z,n
+  const float* whh;  // (3H,H)
+  const float* bhh;  // (3H)
+  float* y;          // (B,T,H)
+  float* q;          // (B,T,H) out (if save): h_{t-1} W_hn^T + b_hn
+  int B, T, H;
+  int save;
+  int bulk;
+};
+
+template <int HP, int G, int BT, int TC, int NST>
+__global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel(FwdParams p) {
+  constexpr int KS = HP / G;  // k values per lane
+  static_assert(KS % 4 == 0, "k-slice must be float4 granular");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int j = tid / G, ql = tid % G;
+  const int H = p.H, T = p.T;
+  const int b0 = blockIdx.x * BT;
+  const int nb = min(BT, p.B - b0);
+
+  // ---- shared memory carve-up ----
+  float* hs = reinterpret_cast<float*>(smem_raw);                         // [2][BT][HP]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * BT * HP);          // [NST] (8-B aligned: 2*BT*HP*4 % 8 == 0)
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128);
+
+  ChunkPipe<3, BT, TC, NST> pipe;
+  pipe.g[0] = pipe.gst[0] = p.gi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | (p.save ? TG_STRM_STORE : 0); pipe.shift[0] = 0;
+  pipe.g[1] = pipe.gst[1] = p.q;  pipe.w[1] = H;     pipe.mode[1] = p.save ? TG_STRM_STORE : 0;                  pipe.shift[1] = 0;
+  pipe.g[2] = pipe.gst[2] = p.y;  pipe.w[2] = H;     pipe.mode[2] = TG_STRM_STORE;                               pipe.shift[2] = 0;
+  pipe.layout();
+  pipe.stages = stages; pipe.full = bars;
+  pipe.T = T; pipe.nb = nb; pipe.b0 = b0; pipe.NC = (T + TC - 1) / TC;
+  pipe.reverse = false; pipe.bulk = p.bulk != 0;
+
+  // ---- W_hh slice into registers (interleaved float4 k-assignment => conflict-free LDS.128 of h) ----
+  float w[3][KS];
+  float bh[3];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    bh[g] = (j < H) ? p.bhh[g * H + j] : 0.f;
+#pragma unroll
+    for (int i = 0; i < KS / 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        int k = (i * G + ql) * 4 + c;
+        w[g][4 * i + c] = (j < H && k < H) ? p.whh[(size_t)(g * H + j) * H + k] : 0.f;
+      }
+  }
+  for (int i = tid; i < 2 * BT * HP; i += HP * G) hs[i] = 0.f;
+  pipe.start();
+  __syncthreads();
+
+  int cur = 0;
+  for (int c = 0; c < pipe.NC; ++c) {
+    pipe.acquire(c);
+    const int s = c % NST;
+    const int tcn = pipe.tcn_of(c);
+    for (int tl = 0; tl < tcn; ++tl) {
+      const float* hc = hs + cur * BT * HP;
+      float* hn = hs + (cur ^ 1) * BT * HP;
+      float acc[BT][3];
+#pragma unroll
+      for (int b = 0; b < BT; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
+#pragma unroll
+      for (int i = 0; i < KS / 4; ++i) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+          const float4 hv = reinterpret_cast<const float4*>(hc + b * HP)[i * G + ql];
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            acc[b][g] = fmaf(w[g][4 * i + 0], hv.x, acc[b][g]);
+            acc[b][g] = fmaf(w[g][4 * i + 1], hv.y, acc[b][g]);
+            acc[b][g] = fmaf(w[g][4 * i + 2], hv.z, acc[b][g]);
+            acc[b][g] = fmaf(w[g][4 * i + 3], hv.w, acc[b][g]);
+          }
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[b][g] = group_sum<G>(acc[b][g]);
+        if (ql == (b % G) && j < H && b < nb) {
+          float* gp = pipe.row(s, 0, b, tl);
+          const float hp = hc[b * HP + j];
+          const float r = sigmoid_acc(gp[j] + acc[b][0] + bh[0]);
+          const float z = sigmoid_acc(gp[H + j] + acc[b][1] + bh[1]);
+          const float qv = acc[b][2] + bh[2];
+          const float n = tanh_acc(gp[2 * H + j] + r * qv);
+          const float h = n + z * (hp - n);
+          hn[b * HP + j] = h;
+          pipe.row(s, 2, b, tl)[j] = h;
+          if (p.save) {
+            gp[j] = r; gp[H + j] = z; gp[2 * H + j] = n;
+            pipe.row(s, 1, b, tl)[j] = qv;
+          }
+        }
+      }
+      if (tl == tcn - 1 && pipe.bulk) fence_async_smem();
+      __syncthreads();
+      cur ^= 1;
+    }
+    pipe.release(c);
+  }
+  pipe.drain();
+}
+
+template <int HP, int G, int BT, int TC, int NST>
+int launch_fwd(cudaStream_t st, const FwdParams& p) {
+  const int widths[3] = {3 * p.H, p.H, p.H};
+  size_t smem = ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128 +
+                (size_t)NST * ChunkPipe<3, BT, TC, NST>::stage_floats_for(widths) * 4;
+  auto kern = gru_fwd_kernel<HP, G, BT, TC, NST>;
+  static thread_local size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { tg_set_error("gru_fwd: smem attr %zu B: %s", smem, cudaGetErrorString(e)); return (int)e; }
+    configured = smem;
+  }
+  dim3 grid((p.B + BT - 1) / BT), block(HP * G);
+  kern<<<grid, block, smem, st>>>(p);
+  return tg_check_launch("gru_fwd");
+}
+
+template <int HP, int G>
+int dispatch_bt(cudaStream_t st, const FwdParams& p, int bt) {
+  constexpr int TC = (HP >= 128) ? 4 : 8, NST = 3;
+  switch (bt) {
+    case 1: return launch_fwd<HP, G, 1, TC, NST>(st, p);
+    case 2: return launch_fwd<HP, G, 2, TC, NST>(st, p);
+    case 4: return launch_fwd<HP, G, 4, TC, NST>(st, p);
+  }
+  tg_set_error("gru_fwd: bad BT %d", bt);
+  return TG_ERR_ARG;
+}
+
+}  // namespace
+
+int tg_pick_bt(int B, int HP, int bt_override) {
+  if (bt_override == 1 || bt_override == 2 || bt_override == 4) return bt_override;
+  const int occ = (HP <= 64) ? 2 : 1;
+  const int cap = tg_num_sms() * occ;
+  if (B <= cap) return 1;
+  if (B <= 2 * cap) return 2;
+  return 4;
+}
+
+int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T,
+                    int H, int flags) {
+  TG_REQUIRE(gi && whh && bhh && y, TG_ERR_ARG, "gru_fwd: null pointer");
+  TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_fwd: bad shape B=%d T=%d H=%d", B, T, H);
+  TG_REQUIRE(H <= 128, TG_ERR_UNSUPPORTED, "gru_fwd: hidden size %d > 128 needs the cluster kernel (not built yet)", H);
+  const int save = (flags & TG_GRU_SAVE) ? 1 : 0;
+  TG_REQUIRE(!save || q, TG_ERR_ARG, "gru_fwd: save requested without q buffer");
+  FwdParams p{gi, whh, bhh, y, q, B, T, H, save, 0};
+  p.bulk = (H % 4 == 0) && tg_aligned16(gi) && tg_aligned16(y) && (!save || tg_aligned16(q)) &&
+           !(flags & TG_GRU_NO_BULK);
+  const int bto = (flags >> 8) & 0xff;
+  if (H <= 32) return dispatch_bt<32, 4>(st, p, tg_pick_bt(B, 32, bto));
+  if (H <= 64) return dispatch_bt<64, 4>(st, p, tg_pick_bt(B, 64, bto));
+  return dispatch_bt<128, 4>(st, p, tg_pick_bt(B, 128, bto));
+}

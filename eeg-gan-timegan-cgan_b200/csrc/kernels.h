@@ -1,0 +1,41 @@
+// Internal C++ entry points behind the C ABI (api.cu forwards to these). Not installed.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+// flags shared with include/timegan_b200.h
+#define TG_GRU_SAVE 1      // forward: keep r,z,n (in place of gi) and q for BPTT
+#define TG_GRU_NO_BULK 2   // force the generic (non-TMA) streaming path (testing)
+#define TG_GRU_DY_LAST 4   // backward: dy is (B,H) and applies to t = T-1 only (discriminator head)
+
+int tg_num_sms();
+int tg_pick_bt(int B, int HP, int bt_override);
+
+int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T,
+                    int H, int flags);
+int tg_gru_bwd_impl(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y,
+                    const float* whh, float* dgi, float* dq, int B, int T, int H, int flags);
+int tg_gru_jvp_fwd_impl(cudaStream_t st, float* gid, const float* rzn, const float* q, const float* y,
+                        const float* whh, float* ydot, float* qdot, int B, int T, int H, int flags);
+int tg_gru_jvp_bwd_impl(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
+                        const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh,
+                        float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags);
+
+// time-batched contractions (FFMA baseline path; fp32 exact)
+int tg_gemm_nt_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
+                    int ldc, int M, int N, int K, int accumulate);
+int tg_gemm_nn_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N,
+                    int K, int accumulate);
+int tg_wgrad_impl(cudaStream_t st, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db,
+                  int M, int N, int K, int a_shift_T, int accumulate, float* ws, size_t ws_bytes);
+size_t tg_wgrad_ws_bytes(int M, int N, int K);
+
+// tensor-core projection (tcgen05 + TMA); returns TG_ERR_UNSUPPORTED for shapes it cannot take
+int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
+                    int ldc, int M, int N, int K, int accumulate);
+
+// column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)
+size_t tg_colsum_ws_bytes(int N);
+int tg_colsum_impl(cudaStream_t st, const float* X, int ld, int M, int N, float* out, int accumulate, float* ws,
+                   size_t ws_bytes);

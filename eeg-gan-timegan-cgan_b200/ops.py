@@ -1,0 +1,327 @@
+"""torch.autograd.Function wrappers around the C ABI (the thin host layer the north_star asks for).
+
+Low-level "stack" helpers run an L-layer GRU stack layer by layer:
+    projection GEMM (time-batched X W_ih^T + b_ih)  ->  persistent recurrent kernel
+and the matching backward / tangent-forward / reverse-over-tangent passes.  They are used directly by the
+fused training steps (train_timegan.disc_step needs the R1 passes) and wrapped in GRUStackFunction for the
+module API of timegan_model.py.
+
+Reference behaviour being reproduced: timeGAN/timegan_model.py:24-34 (GRUStack -> nn.GRU(batch_first=True),
+h0 = 0, returns y only), SURVEY.md Appendix A.1/A.2/A.4 for the math.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import lib, check, ptr, stream_ptr, require_cuda
+
+# process-wide projection mode for the GRU input projections ("fp32" exact, "bf16" tensor-core mode)
+_PROJ_MODE = _lib.PROJ_FP32
+_BT_OVERRIDE = 0  # sequences per CTA override for the recurrent kernels (0 = heuristic)
+
+
+def set_proj_mode(mode: str):
+    global _PROJ_MODE
+    if mode not in ("fp32", "bf16"):
+        raise ValueError("proj mode must be 'fp32' or 'bf16'")
+    _PROJ_MODE = _lib.PROJ_FP32 if mode == "fp32" else _lib.PROJ_BF16
+
+
+def get_proj_mode() -> str:
+    return "fp32" if _PROJ_MODE == _lib.PROJ_FP32 else "bf16"
+
+
+def set_bt_override(bt: int):
+    global _BT_OVERRIDE
+    if bt not in (0, 1, 2, 4):
+        raise ValueError("bt override must be 0, 1, 2 or 4")
+    _BT_OVERRIDE = bt
+
+
+def _flags(base: int = 0) -> int:
+    return base | (_BT_OVERRIDE << 8)
+
+
+class LayerSave:
+    """Activations one layer keeps for its backward pass (all (B,T,*) fp32, contiguous)."""
+    __slots__ = ("inp", "rzn", "q", "y")
+
+    def __init__(self, inp, rzn, q, y):
+        self.inp, self.rzn, self.q, self.y = inp, rzn, q, y
+
+
+def _ws(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw GEMM helpers
+# ------------------------------------------------------------------------------------------------
+def proj(a2d: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out2d: Optional[torch.Tensor] = None,
+         mode: Optional[int] = None, accumulate: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= a[M,K] @ w[N,K]^T + bias."""
+    M, K = a2d.shape
+    N = w.shape[0]
+    if out2d is None:
+        out2d = torch.empty(M, N, dtype=torch.float32, device=a2d.device)
+    check(lib.tg_proj(stream_ptr(), ptr(a2d), a2d.stride(0), ptr(w), w.stride(0), ptr(bias), ptr(out2d),
+                      out2d.stride(0), M, N, K, int(accumulate), _PROJ_MODE if mode is None else mode), "tg_proj")
+    return out2d
+
+
+def dgrad(dg2d: torch.Tensor, w: torch.Tensor, out2d: Optional[torch.Tensor] = None,
+          accumulate: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= dg[M,K] @ w[K,N]."""
+    M, K = dg2d.shape
+    N = w.shape[1]
+    if out2d is None:
+        out2d = torch.empty(M, N, dtype=torch.float32, device=dg2d.device)
+    check(lib.tg_dgrad(stream_ptr(), ptr(dg2d), dg2d.stride(0), ptr(w), w.stride(0), ptr(out2d), out2d.stride(0),
+                       M, N, K, int(accumulate)), "tg_dgrad")
+    return out2d
+
+
+def wgrad(dg2d: torch.Tensor, a2d: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor], n_cols: int,
+          shift_T: int = 0, accumulate: bool = False):
+    """dw[N,K] (+)= dg[:, :N]^T @ a ; db[N] (+)= colsum(dg[:, :N]).  shift_T>0: a row m := a[m-1], 0 at m%T==0."""
+    M = dg2d.shape[0]
+    K = a2d.shape[1]
+    nbytes = lib.tg_wgrad_workspace_bytes(M, n_cols, K)
+    ws = _ws(nbytes, dg2d.device)
+    check(lib.tg_wgrad(stream_ptr(), ptr(dg2d), dg2d.stride(0), ptr(a2d), a2d.stride(0), ptr(dw), dw.stride(0),
+                       ptr(db), M, n_cols, K, shift_T, int(accumulate), ptr(ws), nbytes), "tg_wgrad")
+
+
+def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    M, N = x2d.shape
+    if out is None:
+        out = torch.empty(N, dtype=torch.float32, device=x2d.device)
+    nbytes = lib.tg_colsum_workspace_bytes(N)
+    ws = _ws(nbytes, x2d.device)
+    check(lib.tg_colsum(stream_ptr(), ptr(x2d), x2d.stride(0), M, N, ptr(out), int(accumulate), ptr(ws), nbytes),
+          "tg_colsum")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# GRU stack passes
+# ------------------------------------------------------------------------------------------------
+def _layer_weights(weights: Sequence[torch.Tensor], l: int):
+    return weights[4 * l], weights[4 * l + 1], weights[4 * l + 2], weights[4 * l + 3]
+
+
+def stack_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], save: bool,
+                  dropout_p: float = 0.0, training: bool = False) -> Tuple[torch.Tensor, List[LayerSave]]:
+    """Run the L-layer stack.  weights = [w_ih, w_hh, b_ih, b_hh] * L.  Returns (y_last_layer, saves)."""
+    require_cuda(x, "GRU input")
+    x = x.contiguous()
+    B, T, _ = x.shape
+    L = len(weights) // 4
+    saves: List[LayerSave] = []
+    inp = x
+    for l in range(L):
+        w_ih, w_hh, b_ih, b_hh = _layer_weights(weights, l)
+        H = w_hh.shape[1]
+        gi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=x.device)
+        proj(inp.view(B * T, -1), w_ih, b_ih, gi.view(B * T, 3 * H))
+        y = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
+        q = torch.empty(B, T, H, dtype=torch.float32, device=x.device) if save else None
+        check(lib.tg_gru_fwd(stream_ptr(), ptr(gi), ptr(w_hh), ptr(b_hh), ptr(y), ptr(q), B, T, H,
+                             _flags(_lib.GRU_SAVE if save else 0)), "tg_gru_fwd")
+        if save:
+            saves.append(LayerSave(inp, gi, q, y))
+        inp = y
+        if dropout_p > 0.0 and training and l < L - 1:
+            raise RuntimeError("inter-layer dropout is handled by GRUStack (per-layer calls); not here")
+    return inp, saves
+
+
+def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[torch.Tensor], need_dx: bool,
+                   need_dw: bool, dy_last: bool = False, grads: Optional[List[torch.Tensor]] = None,
+                   accumulate: bool = False):
+    """BPTT through the stack.  dy: (B,T,H) or (B,H) if dy_last.  Returns (dx or None, grads list like weights).
+
+    grads (optional) are pre-allocated tensors shaped like `weights` to write (or accumulate) into.
+    """
+    L = len(saves)
+    B, T, _ = saves[0].y.shape
+    dev = saves[0].y.device
+    if need_dw and grads is None:
+        grads = alloc_like_flat(weights)
+        accumulate = False
+    d = dy.contiguous()
+    last_only = dy_last
+    dx = None
+    for l in reversed(range(L)):
+        sv = saves[l]
+        w_ih, w_hh, _, _ = _layer_weights(weights, l)
+        H = w_hh.shape[1]
+        I = w_ih.shape[1]
+        dgi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
+        dq = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        check(lib.tg_gru_bwd(stream_ptr(), ptr(d), ptr(sv.rzn), ptr(sv.q), ptr(sv.y), ptr(w_hh), ptr(dgi), ptr(dq),
+                             B, T, H, _flags(_lib.GRU_DY_LAST if last_only else 0)), "tg_gru_bwd")
+        last_only = False
+        dgi2 = dgi.view(B * T, 3 * H)
+        if need_dw:
+            g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
+            wgrad(dgi2, sv.inp.view(B * T, I), g_wih, g_bih, 3 * H, 0, accumulate)
+            y2 = sv.y.view(B * T, H)
+            wgrad(dgi2, y2, g_whh[: 2 * H], g_bhh[: 2 * H], 2 * H, T, accumulate)
+            wgrad(dq.view(B * T, H), y2, g_whh[2 * H:], g_bhh[2 * H:], H, T, accumulate)
+        if l > 0 or need_dx:
+            dx = torch.empty(B, T, I, dtype=torch.float32, device=dev)
+            dgrad(dgi2, w_ih, dx.view(B * T, I))
+            d = dx
+    return (dx if need_dx else None), grads
+
+
+class TangentSave:
+    __slots__ = ("xdot", "ta", "qdot", "ydot")
+
+    def __init__(self, xdot, ta, qdot, ydot):
+        self.xdot, self.ta, self.qdot, self.ydot = xdot, ta, qdot, ydot
+
+
+def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Sequence[torch.Tensor]):
+    """Tangent forward with fixed weights.  Returns (ydot_last_layer, tangent saves)."""
+    L = len(saves)
+    B, T, _ = saves[0].y.shape
+    dev = xdot.device
+    tin = xdot.contiguous()
+    tsaves: List[TangentSave] = []
+    for l in range(L):
+        sv = saves[l]
+        w_ih, w_hh, _, _ = _layer_weights(weights, l)
+        H = w_hh.shape[1]
+        gid = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
+        proj(tin.view(B * T, -1), w_ih, None, gid.view(B * T, 3 * H), mode=_lib.PROJ_FP32)
+        ydot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        qdot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        check(lib.tg_gru_jvp_fwd(stream_ptr(), ptr(gid), ptr(sv.rzn), ptr(sv.q), ptr(sv.y), ptr(w_hh), ptr(ydot),
+                                 ptr(qdot), B, T, H, _flags()), "tg_gru_jvp_fwd")
+        tsaves.append(TangentSave(tin, gid, qdot, ydot))
+        tin = ydot
+    return tin, tsaves
+
+
+def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves: List[LayerSave],
+                       tsaves: List[TangentSave], weights: Sequence[torch.Tensor], grads: List[torch.Tensor],
+                       accumulate: bool):
+    """Reverse over (primal + tangent) forward.  hbar_last / hdbar_last: (B,H) adjoints of the last step of the
+    top layer's y / ydot.  Accumulates weight gradients into `grads`; input adjoints are not needed (R1: the
+    stack input and its tangent are constants)."""
+    L = len(saves)
+    B, T, _ = saves[0].y.shape
+    dev = hbar_last.device
+    hb, hdb = hbar_last.contiguous(), hdbar_last.contiguous()
+    last_only = True
+    for l in reversed(range(L)):
+        sv, ts = saves[l], tsaves[l]
+        w_ih, w_hh, _, _ = _layer_weights(weights, l)
+        H = w_hh.shape[1]
+        I = w_ih.shape[1]
+        gib = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
+        gidb = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
+        qb = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        qdb = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        check(lib.tg_gru_jvp_bwd(stream_ptr(), ptr(hb), ptr(hdb), ptr(sv.rzn), ptr(sv.q), ptr(ts.ta), ptr(ts.qdot),
+                                 ptr(sv.y), ptr(ts.ydot), ptr(w_hh), ptr(gib), ptr(qb), ptr(gidb), ptr(qdb), B, T, H,
+                                 _flags(_lib.GRU_DY_LAST if last_only else 0)), "tg_gru_jvp_bwd")
+        last_only = False
+        g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
+        gib2, gidb2 = gib.view(B * T, 3 * H), gidb.view(B * T, 3 * H)
+        y2, yd2 = sv.y.view(B * T, H), ts.ydot.view(B * T, H)
+        # primal path
+        wgrad(gib2, sv.inp.view(B * T, I), g_wih, g_bih, 3 * H, 0, accumulate)
+        wgrad(gib2, y2, g_whh[: 2 * H], g_bhh[: 2 * H], 2 * H, T, accumulate)
+        wgrad(qb.view(B * T, H), y2, g_whh[2 * H:], g_bhh[2 * H:], H, T, accumulate)
+        # tangent path (no bias terms in the tangent)
+        wgrad(gidb2, ts.xdot.view(B * T, I), g_wih, None, 3 * H, 0, True)
+        wgrad(gidb2, yd2, g_whh[: 2 * H], None, 2 * H, T, True)
+        wgrad(qdb.view(B * T, H), yd2, g_whh[2 * H:], None, H, T, True)
+        if l > 0:
+            hb = torch.empty(B, T, I, dtype=torch.float32, device=dev)
+            hdb = torch.empty(B, T, I, dtype=torch.float32, device=dev)
+            dgrad(gib2, w_ih, hb.view(B * T, I))
+            dgrad(gidb2, w_ih, hdb.view(B * T, I))
+
+
+def alloc_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """One allocation carved into views shaped like `tensors` (weight-gradient buffers of a stack)."""
+    total = sum(t.numel() for t in tensors)
+    flat = torch.empty(total, dtype=torch.float32, device=tensors[0].device)
+    out, o = [], 0
+    for t in tensors:
+        n = t.numel()
+        out.append(flat[o:o + n].view(t.shape))
+        o += n
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd Functions (module API)
+# ------------------------------------------------------------------------------------------------
+class GRUStackFunction(torch.autograd.Function):
+    """y = GRUStack(x) for an L-layer stack without inter-layer dropout (timegan_model.py:32-34)."""
+
+    @staticmethod
+    def forward(ctx, x, *weights):
+        need = any(ctx.needs_input_grad)
+        y, saves = stack_forward(x, [w.detach() for w in weights], save=need)
+        ctx.saves = saves
+        ctx.weights = [w.detach() for w in weights]
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        need_dx = ctx.needs_input_grad[0]
+        need_dw = any(ctx.needs_input_grad[1:])
+        dx, grads = stack_backward(dy, ctx.saves, ctx.weights, need_dx, need_dw)
+        ctx.saves = None
+        if not need_dw:
+            grads = [None] * len(ctx.weights)
+        else:
+            grads = [g if n else None for g, n in zip(grads, ctx.needs_input_grad[1:])]
+        return (dx, *grads)
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T + b over the last dim (timegan_model.py:53 Recovery.out; :66/:79 G/S proj when h != z)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        require_cuda(x, "Linear input")
+        x = x.contiguous()
+        K = x.shape[-1]
+        x2 = x.view(-1, K)
+        out = proj(x2, weight.detach(), None if bias is None else bias.detach(), mode=_lib.PROJ_FP32)
+        ctx.save_for_backward(x2, weight)
+        ctx.has_bias = bias is not None
+        return out.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x2, weight = ctx.saved_tensors
+        N, K = weight.shape
+        d2 = dout.contiguous().view(-1, N)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = dgrad(d2, weight.detach()).view(*dout.shape[:-1], K)
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(weight)
+            db = torch.empty(N, dtype=torch.float32, device=weight.device) if ctx.has_bias else None
+            wgrad(d2, x2, dw, db, N)
+        return dx, dw, db
+
+
+def gru_stack(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    return GRUStackFunction.apply(x, *weights)
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    return LinearFunction.apply(x, weight, bias)

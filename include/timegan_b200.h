@@ -1,0 +1,128 @@
+/* timegan_b200.h -- C ABI of libtimegan_b200.so: the B200 (sm_100a) hot path of the TimeGAN training step.
+ *
+ * The reference (Jeniya1378/eeg-gan-timegan-cgan) has no FFI layer: its hot path is the PyTorch calls made
+ * from timeGAN/timegan_model.py and timeGAN/train_timegan.py.  Each entry point below replaces one of those
+ * call sites (cited per function as file:line under /root/reference/timeGAN/); the Python host package
+ * binds them with ctypes inside torch.autograd.Function wrappers.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; all tensors are fp32, contiguous, batch-first (B,T,*).
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch's allocator); the library never
+ *     allocates or frees device memory and never synchronises the device.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - return 0 = ok; negative = argument/shape/alignment error detected before launch (TG_ERR_*);
+ *     positive = cudaError_t from the launch.  tg_last_error() returns a thread-local message.
+ *   - no CPU fallback exists: without a CUDA device every compute call fails with a cudaError.
+ */
+#ifndef TIMEGAN_B200_H
+#define TIMEGAN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_ABI_VERSION 1
+
+#define TG_OK 0
+#define TG_ERR_ARG (-1)
+#define TG_ERR_SHAPE (-2)
+#define TG_ERR_ALIGN (-3)
+#define TG_ERR_UNSUPPORTED (-4)
+
+/* flags of the recurrent kernels (bits 8..15 optionally force sequences-per-CTA to 1, 2 or 4) */
+#define TG_GRU_SAVE 1    /* forward: keep r,z,n (written over gi) and q for the backward pass */
+#define TG_GRU_NO_BULK 2 /* use generic loads/stores instead of cp.async.bulk (testing) */
+#define TG_GRU_DY_LAST 4 /* backward: the output gradient is (B,H) and applies to t = T-1 only */
+
+/* projection precision */
+#define TG_PROJ_FP32 0 /* CUDA-core FFMA, exact fp32 (parity mode, 1e-4) */
+#define TG_PROJ_BF16 1 /* tcgen05 tensor cores, bf16 operands / fp32 accumulate (2e-2 mode) */
+
+int tg_version(void);
+const char* tg_last_error(void);
+int tg_device_sm_count(void);
+
+/* ---- GRU layer, time-batched input projection:  C[M,N] (+)= A[M,K] W[N,K]^T + bias[N] -------------------
+ * Replaces `params.linear_ih(input)` inside at::gru reached from timegan_model.py:33 (GRUStack.forward),
+ * and the head Linears timegan_model.py:53 (Recovery.out), :66 (Generator.proj), :79 (Supervisor.proj).
+ * bias may be NULL.  mode: TG_PROJ_FP32 | TG_PROJ_BF16. */
+int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
+            int M, int N, int K, int accumulate, int mode);
+
+/* ---- dX[M,N] (+)= dG[M,K] W[K,N]  (autograd of the projection w.r.t. its input; loss.backward() at
+ * train_timegan.py:140,159,219,267) */
+int tg_dgrad(void* stream, const float* dG, int ldg, const float* W, int ldw, float* dX, int ldx, int M, int N, int K,
+             int accumulate);
+
+/* ---- weight gradients: dW[N,K] (+)= dG[M,N]^T A[M,K];  db[N] (+)= colsum(dG)  (db may be NULL) -------------
+ * M = B*T.  a_shift_T > 0: A row m is taken as A[m-1] and as zero when m % a_shift_T == 0 (h_{t-1} read from
+ * the layer output y).  Deterministic split-M reduction through `ws` (>= tg_wgrad_workspace_bytes). */
+size_t tg_wgrad_workspace_bytes(int M, int N, int K);
+int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
+             int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes);
+
+/* ---- persistent fused GRU layer forward (timegan_model.py:32-34 -> nn.GRU per-timestep loop) --------------
+ * gi (B,T,3H) holds X W_ih^T + b_ih on entry; with TG_GRU_SAVE it holds r,z,n on exit and q (B,T,H) receives
+ * h_{t-1} W_hn^T + b_hn.  y (B,T,H) receives h_t.  h0 = 0 (the reference never passes an initial state). */
+int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, float* y, float* q, int B, int T, int H,
+               int flags);
+
+/* ---- persistent BPTT of one layer (autograd of the nn.GRU loop; train_timegan.py:140,159,219,267,200) -----
+ * in: dy (B,T,H) [or (B,H) with TG_GRU_DY_LAST], saved rzn,q, layer output y.  out: dgi (B,T,3H) =
+ * [dar,daz,dan] (gradient of gi; also rows 0..2H of dGH) and dq (B,T,H) = dan*r (rows 2H..3H of dGH). */
+int tg_gru_bwd(void* stream, const float* dy, const float* rzn, const float* q, const float* y, const float* w_hh,
+               float* dgi, float* dq, int B, int T, int H, int flags);
+
+/* ---- R1 penalty (train_timegan.py:198-202) without generic double backward: tangent forward ... ----------
+ * gid (B,T,3H) holds xdot W_ih^T on entry and the tangent pre-activations a_r,a_z,a_n on exit. */
+int tg_gru_jvp_fwd(void* stream, float* gid, const float* rzn, const float* q, const float* y, const float* w_hh,
+                   float* ydot, float* qdot, int B, int T, int H, int flags);
+/* ... and its reverse.  hbar/hdbar: adjoints of y / ydot ((B,H) with TG_GRU_DY_LAST).  Outputs are the
+ * adjoints of the primal (gib,qb) and tangent (gidb,qdb) gate pre-activations, laid out like dgi/dq. */
+int tg_gru_jvp_bwd(void* stream, const float* hbar, const float* hdbar, const float* rzn, const float* q,
+                   const float* ta, const float* qdot, const float* y, const float* ydot, const float* w_hh,
+                   float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags);
+
+/* ---- losses (train_timegan.py:72-74 recon, :156-158 sup MSE, :79-80 first difference, :82-126 cov/ACF) ----
+ * Scalars live on the device (float*), so no host synchronisation is needed between kernels. */
+size_t tg_reduce_workspace_bytes(void);
+int tg_sqdiff_sum(void* stream, const float* a, const float* b, long long n, float* out, void* ws, size_t ws_bytes);
+int tg_scaled_diff(void* stream, const float* a, const float* b, const float* coef, float* out, long long n,
+                   int accumulate); /* out (+)= coef[0]*(a-b) */
+int tg_diff1_sum(void* stream, const float* h, int B, int T, int H, float* out, void* ws, size_t ws_bytes);
+int tg_diff1_grad(void* stream, const float* h, const float* coef, float* out, int B, int T, int H, int accumulate);
+int tg_center_scale(void* stream, const float* x, const float* mean, const float* scale, float* out, long long rows,
+                    int C); /* out = (x-mean[c])*scale[c]; scale may be NULL */
+/* out[N] (+)= column sums of X (M rows, leading dimension ld): per-channel means for cov/ACF, bias gradients */
+size_t tg_colsum_workspace_bytes(int N);
+int tg_colsum(void* stream, const float* X, int ld, int M, int N, float* out, int accumulate, void* ws,
+              size_t ws_bytes);
+int tg_acf_fwd(void* stream, const float* xz, int B, int T, int C, int L, float* part /* (B,L,C) */);
+int tg_acf_bwd(void* stream, const float* xz, const float* S /* (L,C) */, int B, int T, int C, int L,
+               float* gz /* (B,T,C) */, float* stat /* (B,2,C) */);
+int tg_acf_bwd_final(void* stream, const float* gz, const float* xz, const float* mean_gz, const float* kc,
+                     const float* inv_s, float* dx, long long rows, int C, int accumulate);
+
+/* ---- clip_grad_norm_ + Adam (train_timegan.py:141-142,160-161,220-221,268-272) ---------------------------
+ * Host arrays of n device pointers / element counts.  tg_sumsq writes sum g^2 over all tensors to a device
+ * scalar; tg_adam applies g*grad_scale, the global-norm clip (max_norm <= 0: none) and one Adam step. */
+size_t tg_sumsq_workspace_bytes(int n, const long long* sizes);
+int tg_sumsq(void* stream, int n, const float* const* grads, const long long* sizes, float* out_sumsq, void* ws,
+             size_t ws_bytes);
+int tg_adam(void* stream, int n, float* const* params, const float* const* grads, float* const* exp_avg,
+            float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr, float beta1,
+            float beta2, float eps, int step, float grad_scale);
+
+/* ---- noise (train_timegan.py:64-65 sample_noise, :46-47 add_instance_noise, :40-43 smooth_labels) --------
+ * Philox4x32-10 keyed by (seed, offset); each call consumes ceil(n/4) counter values. */
+int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,
+                   float hi);
+int tg_rng_add_normal(void* stream, const float* in /* may be NULL */, float* out, long long n, float std,
+                      unsigned long long seed, unsigned long long offset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIMEGAN_B200_H */
