@@ -1,0 +1,173 @@
+"""GPU parity of the persistent GRU kernels (forward, BPTT, tangent forward, reverse-over-tangent) through the
+C ABI, against torch.nn.GRU + autograd on the CPU in fp32 -- the arithmetic path the reference takes from
+timegan_model.py:32-34 -- and against the explicit recurrences of oracle/gru_math.py in fp64.
+
+Tolerance: fp32 forward and gradients within 1e-4 normwise relative (BASELINE.json north_star)."""
+import pytest
+import torch
+
+from parity_util import relerr, make_gru, flat_weights
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+SHAPES = [
+    # B, T, I, H, L
+    (3, 17, 5, 8, 2),
+    (1, 1, 14, 24, 1),       # single step
+    (5, 33, 14, 6, 2),       # H % 4 != 0 -> generic (non-bulk) streaming path
+    (4, 100, 28, 56, 1),     # reference default dims (z=28, h=56, L=1)
+    (32, 768, 14, 24, 3),    # config c1 embedder
+    (7, 768, 24, 24, 3),     # ragged batch (N % B != 0 tail)
+    (9, 200, 14, 64, 3),     # config c2 dims
+    (3, 96, 14, 128, 2),     # config c3 dims
+]
+
+
+def _ops():
+    from timegan_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("B,T,I,H,L", SHAPES)
+def test_forward_matches_nn_gru(B, T, I, H, L):
+    ops = _ops()
+    m = make_gru(I, H, L, seed=B + T)
+    x = torch.rand(B, T, I, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        y_ref, _ = m(x)
+    dev = torch.device("cuda:0")
+    y, _ = ops.stack_forward(x.to(dev), flat_weights(m, dev), save=False)
+    assert relerr(y, y_ref) < TOL
+    y2, saves = ops.stack_forward(x.to(dev), flat_weights(m, dev), save=True)
+    assert relerr(y2, y_ref) < TOL
+    assert len(saves) == L
+
+
+@pytest.mark.parametrize("B,T,I,H,L", SHAPES)
+def test_bptt_matches_autograd(B, T, I, H, L):
+    ops = _ops()
+    m = make_gru(I, H, L, seed=3 * B + T)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(B, T, I, generator=g, requires_grad=True)
+    y_ref, _ = m(x)
+    dy = torch.randn(B, T, H, generator=g)
+    ref = torch.autograd.grad((y_ref * dy).sum(), [x] + list(m.parameters()))
+    dev = torch.device("cuda:0")
+    w = flat_weights(m, dev)
+    _, saves = ops.stack_forward(x.detach().to(dev), w, save=True)
+    dx, grads = ops.stack_backward(dy.to(dev), saves, w, need_dx=True, need_dw=True)
+    assert relerr(dx, ref[0]) < TOL
+    for k, gk in enumerate(grads):
+        assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
+
+
+@pytest.mark.parametrize("bt", [1, 2, 4])
+@pytest.mark.parametrize("H", [24, 64, 128])
+def test_sequences_per_cta_variants(bt, H):
+    """Every BT instantiation of the forward/backward kernels gives the same answer (incl. a ragged last CTA)."""
+    ops = _ops()
+    B, T, I, L = 7, 40, 14, 2
+    m = make_gru(I, H, L, seed=H + bt)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(B, T, I, generator=g, requires_grad=True)
+    y_ref, _ = m(x)
+    dy = torch.randn(B, T, H, generator=g)
+    ref = torch.autograd.grad((y_ref * dy).sum(), [x] + list(m.parameters()))
+    dev = torch.device("cuda:0")
+    w = flat_weights(m, dev)
+    ops.set_bt_override(bt)
+    try:
+        y, saves = ops.stack_forward(x.detach().to(dev), w, save=True)
+        dx, grads = ops.stack_backward(dy.to(dev), saves, w, need_dx=True, need_dw=True)
+    finally:
+        ops.set_bt_override(0)
+    assert relerr(y, y_ref) < TOL
+    assert relerr(dx, ref[0]) < TOL
+    for k, gk in enumerate(grads):
+        assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
+
+
+def test_last_step_only_gradient():
+    """Discriminator pattern (timegan_model.py:97): only y[:, -1] feeds the loss."""
+    ops = _ops()
+    B, T, I, H, L = 6, 64, 24, 24, 3
+    m = make_gru(I, H, L, seed=11)
+    g = torch.Generator().manual_seed(6)
+    x = torch.rand(B, T, I, generator=g, requires_grad=True)
+    y_ref, _ = m(x)
+    dl = torch.randn(B, H, generator=g)
+    ref = torch.autograd.grad((y_ref[:, -1] * dl).sum(), [x] + list(m.parameters()))
+    dev = torch.device("cuda:0")
+    w = flat_weights(m, dev)
+    _, saves = ops.stack_forward(x.detach().to(dev), w, save=True)
+    dx, grads = ops.stack_backward(dl.to(dev), saves, w, need_dx=True, need_dw=True, dy_last=True)
+    assert relerr(dx, ref[0]) < TOL
+    for k, gk in enumerate(grads):
+        assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
+
+
+def test_autograd_function_module_api():
+    """timegan_b200.GRUStack == reference GRUStack (nn.GRU) through torch autograd."""
+    import timegan_b200 as tg
+    B, T, I, H, L = 4, 50, 14, 24, 3
+    m = make_gru(I, H, L, seed=21)
+    ours = tg.GRUStack(I, H, L, dropout=0.0)
+    ours.rnn.load_state_dict(m.state_dict())
+    ours = ours.cuda()
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(B, T, I, generator=g)
+    xr = x.clone().requires_grad_(True)
+    y_ref, _ = m(xr)
+    (y_ref ** 2).sum().backward()
+    xo = x.clone().cuda().requires_grad_(True)
+    y = ours(xo)
+    (y ** 2).sum().backward()
+    assert relerr(y, y_ref) < TOL
+    assert relerr(xo.grad, xr.grad) < TOL
+    for (n, p), (_, q) in zip(ours.rnn.named_parameters(), m.named_parameters()):
+        assert relerr(p.grad, q.grad) < TOL, n
+
+
+@pytest.mark.parametrize("B,T,I,H,L", [(3, 12, 5, 8, 2), (4, 64, 24, 24, 3), (2, 30, 14, 64, 1), (2, 20, 14, 128, 2)])
+def test_tangent_forward_and_reverse_match_oracle(B, T, I, H, L):
+    """R1 building blocks (train_timegan.py:198-202 restated per SURVEY.md A.4) vs oracle/gru_math.py in fp64."""
+    from oracle import gru_math as gm
+    ops = _ops()
+    m = make_gru(I, H, L, seed=31, scale=0.5)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(B, T, I, generator=g)
+    v = torch.randn(B, T, I, generator=g)
+    hb_last = torch.randn(B, H, generator=g)
+    hdb_last = torch.randn(B, H, generator=g)
+    # ---- oracle, fp64 ----
+    md = m.double()
+    lw = lambda l: [getattr(md, f"{n}_l{l}").detach() for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    acts, saves, tacts, tsaves = [], [], [], []
+    inp, tin = x.double(), v.double()
+    for l in range(L):
+        w_ih, w_hh, b_ih, b_hh = lw(l)
+        y, sv = gm.gru_layer_fwd(inp, w_ih, w_hh, b_ih, b_hh)
+        yd, ts = gm.gru_layer_jvp(tin, y, sv, w_ih, w_hh)
+        acts.append((inp, y)); saves.append(sv); tacts.append((tin, yd)); tsaves.append(ts)
+        inp, tin = y, yd
+    ydot_ref = tin
+    hb = torch.zeros(B, T, H, dtype=torch.float64); hb[:, -1] = hb_last.double()
+    hdb = torch.zeros(B, T, H, dtype=torch.float64); hdb[:, -1] = hdb_last.double()
+    ref = {}
+    for l in reversed(range(L)):
+        w_ih, w_hh, _, _ = lw(l)
+        hb, hdb, dWi, dWh, dbi, dbh = gm.gru_layer_jvp_bwd(hb, hdb, acts[l][0], tacts[l][0], acts[l][1], tacts[l][1],
+                                                           saves[l], tsaves[l], w_ih, w_hh)
+        ref[l] = (dWi, dWh, dbi, dbh)
+    # ---- CUDA ----
+    dev = torch.device("cuda:0")
+    w = flat_weights(m.float(), dev)
+    _, sv_c = ops.stack_forward(x.to(dev), w, save=True)
+    ydot, ts_c = ops.stack_jvp_forward(v.to(dev), sv_c, w)
+    assert relerr(ydot, ydot_ref) < TOL
+    grads = [torch.zeros_like(t) for t in w]
+    ops.stack_jvp_backward(hb_last.to(dev), hdb_last.to(dev), sv_c, ts_c, w, grads, accumulate=True)
+    for l in range(L):
+        for k in range(4):
+            assert relerr(grads[4 * l + k], ref[l][k]) < TOL, (l, k)

@@ -3,7 +3,16 @@ including the R1 double backward of train_timegan.py:198-202 restated as JVP + r
 import torch
 from oracle import gru_math as gm
 
-torch.set_default_dtype(torch.float64)
+import pytest
+
+
+@pytest.fixture(autouse=True)
+def _fp64_default():
+    """fp64 for these tests only (a module-level set_default_dtype would leak into every other test)."""
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(old)
 
 
 def _mk(I, H, L, seed=0):
