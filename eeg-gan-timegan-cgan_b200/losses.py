@@ -11,6 +11,8 @@ Scalars stay on the device; nothing here synchronises with the host.  Under data
 sufficient statistics (sums, Gram matrices, lagged products) are all-reduced through `dist.allreduce_stats`
 between the kernel stages so every rank evaluates the GLOBAL-batch loss.
 """
+import ctypes as _C
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -29,6 +31,18 @@ def _sqdiff_sum(a, b):
     ws, n = _red_ws(a.device)
     check(lib.tg_sqdiff_sum(stream_ptr(), ptr(a), ptr(b), a.numel(), ptr(out), ptr(ws), n), "tg_sqdiff_sum")
     return out
+
+
+def sumsq(t):
+    """sum(t^2) as a device scalar (fixed-order fp64 partials; the R1 norm of train_timegan.py:201)."""
+    t = t.contiguous()
+    out = torch.empty(1, dtype=torch.float32, device=t.device)
+    sizes = (_C.c_longlong * 1)(t.numel())
+    ptrs = (_C.c_void_p * 1)(t.data_ptr())
+    nbytes = lib.tg_sumsq_workspace_bytes(1, sizes)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=t.device)
+    check(lib.tg_sumsq(stream_ptr(), 1, ptrs, sizes, ptr(out), ptr(ws), nbytes), "tg_sumsq")
+    return out.reshape(())
 
 
 class _ReconLoss(torch.autograd.Function):

@@ -51,6 +51,11 @@ class LayerSave:
     def __init__(self, inp, rzn, q, y):
         self.inp, self.rzn, self.q, self.y = inp, rzn, q, y
 
+    def narrow(self, start: int, length: int) -> "LayerSave":
+        """Batch slice [start, start+length) as views (contiguous: the batch is the leading dimension)."""
+        f = lambda t: t.narrow(0, start, length)
+        return LayerSave(f(self.inp), f(self.rzn), f(self.q), f(self.y))
+
 
 def _ws(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
@@ -113,8 +118,11 @@ def _layer_weights(weights: Sequence[torch.Tensor], l: int):
 
 
 def stack_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], save: bool,
-                  dropout_p: float = 0.0, training: bool = False) -> Tuple[torch.Tensor, List[LayerSave]]:
-    """Run the L-layer stack.  weights = [w_ih, w_hh, b_ih, b_hh] * L.  Returns (y_last_layer, saves)."""
+                  masks: Optional[Sequence[torch.Tensor]] = None) -> Tuple[torch.Tensor, List[LayerSave]]:
+    """Run the L-layer stack.  weights = [w_ih, w_hh, b_ih, b_hh] * L.  Returns (y_last_layer, saves).
+
+    masks (optional, L-1 tensors (B,T,H) already scaled by 1/(1-p)): inter-layer dropout of
+    nn.GRU(dropout=p) in train mode (timegan_model.py:27-30) -- layer l+1 reads y_l * masks[l]."""
     require_cuda(x, "GRU input")
     x = x.contiguous()
     B, T, _ = x.shape
@@ -133,14 +141,14 @@ def stack_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], save: bool,
         if save:
             saves.append(LayerSave(inp, gi, q, y))
         inp = y
-        if dropout_p > 0.0 and training and l < L - 1:
-            raise RuntimeError("inter-layer dropout is handled by GRUStack (per-layer calls); not here")
+        if masks is not None and l < L - 1:
+            inp = y * masks[l]
     return inp, saves
 
 
 def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[torch.Tensor], need_dx: bool,
                    need_dw: bool, dy_last: bool = False, grads: Optional[List[torch.Tensor]] = None,
-                   accumulate: bool = False):
+                   accumulate: bool = False, masks: Optional[Sequence[torch.Tensor]] = None):
     """BPTT through the stack.  dy: (B,T,H) or (B,H) if dy_last.  Returns (dx or None, grads list like weights).
 
     grads (optional) are pre-allocated tensors shaped like `weights` to write (or accumulate) into.
@@ -175,6 +183,8 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
             dx = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             dgrad(dgi2, w_ih, dx.view(B * T, I))
             d = dx
+            if masks is not None and l > 0:
+                d = dx * masks[l - 1]
     return (dx if need_dx else None), grads
 
 
@@ -185,7 +195,8 @@ class TangentSave:
         self.xdot, self.ta, self.qdot, self.ydot = xdot, ta, qdot, ydot
 
 
-def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Sequence[torch.Tensor]):
+def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Sequence[torch.Tensor],
+                      masks: Optional[Sequence[torch.Tensor]] = None):
     """Tangent forward with fixed weights.  Returns (ydot_last_layer, tangent saves)."""
     L = len(saves)
     B, T, _ = saves[0].y.shape
@@ -204,12 +215,14 @@ def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Seque
                                  ptr(qdot), B, T, H, _flags()), "tg_gru_jvp_fwd")
         tsaves.append(TangentSave(tin, gid, qdot, ydot))
         tin = ydot
+        if masks is not None and l < L - 1:
+            tin = ydot * masks[l]
     return tin, tsaves
 
 
 def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves: List[LayerSave],
                        tsaves: List[TangentSave], weights: Sequence[torch.Tensor], grads: List[torch.Tensor],
-                       accumulate: bool):
+                       accumulate: bool, masks: Optional[Sequence[torch.Tensor]] = None):
     """Reverse over (primal + tangent) forward.  hbar_last / hdbar_last: (B,H) adjoints of the last step of the
     top layer's y / ydot.  Accumulates weight gradients into `grads`; input adjoints are not needed (R1: the
     stack input and its tangent are constants)."""
@@ -247,6 +260,8 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
             hdb = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             dgrad(gib2, w_ih, hb.view(B * T, I))
             dgrad(gidb2, w_ih, hdb.view(B * T, I))
+            if masks is not None:
+                hb, hdb = hb * masks[l - 1], hdb * masks[l - 1]
 
 
 def alloc_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
@@ -265,28 +280,33 @@ def alloc_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
 # autograd Functions (module API)
 # ------------------------------------------------------------------------------------------------
 class GRUStackFunction(torch.autograd.Function):
-    """y = GRUStack(x) for an L-layer stack without inter-layer dropout (timegan_model.py:32-34)."""
+    """y = GRUStack(x) for an L-layer stack (timegan_model.py:32-34).
+
+    last_only: return only y[:, -1, :] (the discriminator head reads nothing else, timegan_model.py:97); the
+    backward then seeds BPTT at t = T-1 instead of streaming a (B,T,H) gradient that is zero everywhere else.
+    masks: None or a tuple of L-1 scaled inter-layer dropout masks (constants)."""
 
     @staticmethod
-    def forward(ctx, x, *weights):
+    def forward(ctx, x, last_only, masks, *weights):
         need = any(ctx.needs_input_grad)
-        y, saves = stack_forward(x, [w.detach() for w in weights], save=need)
-        ctx.saves = saves
-        ctx.weights = [w.detach() for w in weights]
-        return y
+        wd = [w.detach() for w in weights]
+        y, saves = stack_forward(x, wd, save=need, masks=masks)
+        ctx.saves, ctx.weights, ctx.masks, ctx.last_only = saves, wd, masks, bool(last_only)
+        return y[:, -1, :].contiguous() if last_only else y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         need_dx = ctx.needs_input_grad[0]
-        need_dw = any(ctx.needs_input_grad[1:])
-        dx, grads = stack_backward(dy, ctx.saves, ctx.weights, need_dx, need_dw)
+        need_dw = any(ctx.needs_input_grad[3:])
+        dx, grads = stack_backward(dy, ctx.saves, ctx.weights, need_dx, need_dw, dy_last=ctx.last_only,
+                                   masks=ctx.masks)
         ctx.saves = None
         if not need_dw:
             grads = [None] * len(ctx.weights)
         else:
-            grads = [g if n else None for g, n in zip(grads, ctx.needs_input_grad[1:])]
-        return (dx, *grads)
+            grads = [g if n else None for g, n in zip(grads, ctx.needs_input_grad[3:])]
+        return (dx, None, None, *grads)
 
 
 class LinearFunction(torch.autograd.Function):
@@ -319,8 +339,15 @@ class LinearFunction(torch.autograd.Function):
         return dx, dw, db
 
 
-def gru_stack(x: torch.Tensor, weights: Sequence[torch.Tensor]) -> torch.Tensor:
-    return GRUStackFunction.apply(x, *weights)
+def gru_stack(x: torch.Tensor, weights: Sequence[torch.Tensor], last_only: bool = False,
+              masks: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+    return GRUStackFunction.apply(x, last_only, None if masks is None else tuple(masks), *weights)
+
+
+def dropout_masks(B: int, T: int, H: int, n: int, p: float, device) -> List[torch.Tensor]:
+    """n scaled Bernoulli masks (keep prob 1-p, scale 1/(1-p)) like nn.GRU's inter-layer dropout."""
+    keep = 1.0 - p
+    return [torch.bernoulli(torch.full((B, T, H), keep, dtype=torch.float32, device=device)) / keep for _ in range(n)]
 
 
 def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:

@@ -59,6 +59,7 @@ class FusedAdam(torch.optim.Optimizer):
 
         Returns the device scalar sum g^2 (before scaling) when clipping, else None.
         """
+        self._opt_called = True  # lr_scheduler's "scheduler before optimizer" check looks at this flag
         all_params = [p for g in self.param_groups for p in g["params"] if p.grad is not None]
         if not all_params:
             return None

@@ -52,19 +52,24 @@ class FusedGRU(nn.Module):
         hi = self.num_layers if hi is None else hi
         return [getattr(self, n) for n in self._flat_names[4 * lo:4 * hi]]
 
-    def forward(self, x, hx=None):
+    def dropout_masks(self, x):
+        """Inter-layer dropout masks for this call (None when inactive: eval mode, p = 0 or one layer)."""
+        p = self.dropout if (self.training and self.num_layers > 1) else 0.0
+        if p <= 0.0:
+            return None
+        return ops.dropout_masks(x.shape[0], x.shape[1], self.hidden_size, self.num_layers - 1, p, x.device)
+
+    def forward(self, x, hx=None, last_only: bool = False, frozen: bool = False):
+        """Returns (y, None) like nn.GRU (h_n is not produced: the reference discards it, timegan_model.py:33).
+
+        last_only: y is (B,H) = the last timestep only.  frozen: treat the weights as constants (no weight
+        gradients; the input gradient still flows) -- the discriminator inside gen_step."""
         if hx is not None:
             raise NotImplementedError("FusedGRU: the reference never passes an initial state (h0 = 0)")
-        p = self.dropout if (self.training and self.num_layers > 1) else 0.0
-        if p == 0.0:
-            y = ops.gru_stack(x, self.layer_weights())
-        else:
-            # inter-layer dropout (timegan_model.py:29): layer-by-layer with a mask in between
-            y = x
-            for l in range(self.num_layers):
-                y = ops.gru_stack(y, self.layer_weights(l, l + 1))
-                if l < self.num_layers - 1:
-                    y = torch.nn.functional.dropout(y, p, True)
+        w = self.layer_weights()
+        if frozen:
+            w = [t.detach() for t in w]
+        y = ops.gru_stack(x, w, last_only=last_only, masks=self.dropout_masks(x))
         return y, None
 
     def extra_repr(self):
@@ -147,8 +152,11 @@ class Supervisor(_LatentStack):
 class Discriminator(nn.Module):
     """H or H_hat -> prob(real) (timegan_model.py:86-98): last step -> spectral-norm Linear -> sigmoid.
 
-    The (B,H)x(H,1) head is host-side torch (legacy spectral_norm hook, same buffers/keys as the reference).
-    """
+    `fc` is registered through torch.nn.utils.spectral_norm exactly like the reference, so the parameters and
+    buffers (`fc.bias`, `fc.weight_orig`, `fc.weight_u`, `fc.weight_v`) and their state_dict keys are the
+    reference's.  The (B,H)x(H,1) head itself is evaluated by `head()` below, which restates the legacy
+    spectral-norm hook (one power iteration per call in train mode, eps 1e-12) so the training steps can
+    differentiate it separately from the GRU stack (R1)."""
 
     def __init__(self, z_dim: int, hidden_dim: int = 32, num_layers: int = 2, dropout: float = 0.1):
         super().__init__()
@@ -156,12 +164,27 @@ class Discriminator(nn.Module):
         self.fc = U.spectral_norm(nn.Linear(hidden_dim, 1))
         self.sigmoid = nn.Sigmoid()
 
-    def head(self, last):
-        return self.sigmoid(self.fc(last))
+    def sn_weight(self, frozen: bool = False):
+        """w / sigma with sigma = u^T W v after one power iteration when training (legacy spectral_norm)."""
+        w = self.fc.weight_orig.detach() if frozen else self.fc.weight_orig
+        u, v = self.fc.weight_u, self.fc.weight_v
+        if self.training:
+            with torch.no_grad():
+                wm = self.fc.weight_orig.detach()
+                v.copy_(torch.nn.functional.normalize(torch.mv(wm.t(), u), dim=0, eps=1e-12))
+                u.copy_(torch.nn.functional.normalize(torch.mv(wm, v), dim=0, eps=1e-12))
+            u, v = u.clone(), v.clone()
+        sigma = torch.dot(u, torch.mv(w, v))
+        return w / sigma
 
-    def forward(self, h):
-        y = self.rnn(h)
-        return self.head(y[:, -1, :])
+    def head(self, last, frozen: bool = False):
+        """(B,H) last hidden state -> (B,1) probability."""
+        b = self.fc.bias.detach() if frozen else self.fc.bias
+        return self.sigmoid(torch.nn.functional.linear(last, self.sn_weight(frozen), b))
+
+    def forward(self, h, frozen: bool = False):
+        last, _ = self.rnn.rnn(h, last_only=True, frozen=frozen)
+        return self.head(last, frozen)
 
 
 class TimeGAN(nn.Module):

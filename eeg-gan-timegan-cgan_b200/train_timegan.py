@@ -1,0 +1,554 @@
+"""B200-native drop-in for timeGAN/train_timegan.py: same function names, signatures, defaults, CLI flags,
+log/checkpoint schema -- every GRU pass, loss and optimiser update runs in the sm_100a kernels of csrc/.
+
+Reference map (file:line under /root/reference/timeGAN/train_timegan.py):
+    set_seeds 21-26 · device_autoselect 29-30 · make_loader 33-37 · smooth_labels 40-43 · add_instance_noise 46-47
+    adaptive_dims 50-55 · save_ckpt 58-61 · sample_noise 64-65 · losses 70-126 · phase_autoencoder 131-144
+    phase_supervisor 147-163 · disc_step 166-225 · gen_step 228-276 · train_single_npz 281-422 · main 427-495
+
+What is different by design (B200-first, results identical):
+  * disc_step never builds a double-backward graph: R1 (tt:198-202) is evaluated as dX-only BPTT -> tangent
+    forward -> reverse-over-tangent, real and fake halves share one 2B-batch D forward.
+  * no host synchronisation inside a step: the throttle scale (tt:204-216) is computed on the device; with
+    `sync=False` the step functions return device scalars instead of Python floats.
+  * gen_step treats the discriminator's weights as constants (the reference computes and discards their
+    gradients, tt:267 / SURVEY.md App. D item 8).
+  * optional keyword-only extras, all defaulting to the reference's behaviour: `noise=` (replay host draws for
+    parity), `sync=`, `z_dim=/hidden_dim=` overrides of adaptive_dims, `log_every=`, data-parallel training when
+    launched under torchrun.
+There is no CPU path: a CPU tensor or a missing libtimegan_b200.so raises.
+"""
+import csv
+import math
+from pathlib import Path
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as optim
+from torch.utils.data import DataLoader, TensorDataset
+
+from . import dist as _dist
+from . import losses as _losses
+from . import noise as _noise
+from . import ops
+from .optim import FusedAdam, clip_and_step
+from .timegan_model import TimeGAN
+
+
+# ---------------------- Utilities (tt:21-65) ----------------------
+
+def set_seeds(seed: int = 42):
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def device_autoselect():
+    if not torch.cuda.is_available():
+        raise RuntimeError("timegan_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def make_loader(X: np.ndarray, batch_size: int) -> DataLoader:
+    tens = torch.tensor(X, dtype=torch.float32)
+    ds = TensorDataset(tens)
+    return DataLoader(ds, batch_size=batch_size, shuffle=True, drop_last=False, pin_memory=True, num_workers=0)
+
+
+class HostReplayNoise:
+    """Draws every random tensor from torch's global CPU generator with the reference's calls, in the
+    reference's order, then moves it to the device.  A run seeded like a CPU run of the
+    reference therefore sees bit-identical noise -- the parity mode of the tests and golden curves."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def rand(self, *shape):
+        return torch.rand(*shape).to(self.device)
+
+    def randn_like(self, h, time_major: bool = False):
+        """torch.randn_like on a CPU tensor with the strides the reference's tensor has at that call site:
+        nn.GRU(batch_first=True) returns a transposed view of a (T,B,H) buffer on the CPU, and randn_like
+        fills a non-contiguous tensor through a different (serial) sampling path than a contiguous one, so
+        the replay has to reproduce the layout, not just the shape."""
+        if time_major and h.dim() == 3:
+            B, T, H = h.shape
+            like = torch.empty(T, B, H).transpose(0, 1)
+        else:
+            like = torch.empty(h.shape)
+        return torch.randn_like(like).to(self.device)
+
+
+class _DeviceNoiseAdapter:
+    """Production noise: Philox kernels of csrc/rng.cu (statistically equivalent, no host work)."""
+
+    def __init__(self, src: "_noise.DeviceNoise"):
+        self.src, self.device = src, src.device
+
+    def rand(self, *shape):
+        return self.src.rand(*shape)
+
+    def randn_like(self, h, time_major: bool = False):
+        return self.src.add_randn(torch.zeros_like(h), 1.0)
+
+
+_DEFAULT_NOISE: Dict[str, _DeviceNoiseAdapter] = {}
+
+
+def _noise_source(noise, device):
+    if noise is not None:
+        return noise
+    key = str(device)
+    if key not in _DEFAULT_NOISE:
+        _DEFAULT_NOISE[key] = _DeviceNoiseAdapter(_noise.DeviceNoise(torch.initial_seed() + 7919 * _dist.rank(), device))
+    return _DEFAULT_NOISE[key]
+
+
+def smooth_labels(size: int, smooth: float, device, noise=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    nz = _noise_source(noise, device)
+    real = (1.0 - smooth) + smooth * nz.rand(size, 1)
+    fake = smooth * nz.rand(size, 1)
+    return real, fake
+
+
+def add_instance_noise(h: torch.Tensor, std: float, noise=None, time_major: bool = False) -> torch.Tensor:
+    """tt:46-47.  `time_major` only matters to host-replayed noise (layout of the reference's tensor)."""
+    if std <= 0:
+        return h
+    return h + std * _noise_source(noise, h.device).randn_like(h, time_major)
+
+
+def _latent_is_gru_view(model) -> bool:
+    """True when supervisor output is the raw GRU output (proj is Identity, tm:79), i.e. a time-major view in
+    the reference; with a Linear projection the reference's tensor is batch-major contiguous."""
+    return isinstance(model.supervisor.proj, nn.Identity)
+
+
+def adaptive_dims(x_dim: int, seq_len: int) -> Tuple[int, int]:
+    z = max(16, min(64, x_dim * 2))
+    h = max(32, min(128, x_dim * 4))
+    if seq_len > 800:
+        z = min(64, z + 8)
+        h = min(128, h + 16)
+    return z, h
+
+
+def save_ckpt(path: Path, model: TimeGAN, optG, optD, step: int, meta: Dict):
+    state = {"step": step, "model": model.state_dict(), "optG": optG.state_dict(), "optD": optD.state_dict(),
+             "meta": meta}
+    torch.save(state, path)
+
+
+def sample_noise(batch_size: int, seq_len: int, z_dim: int, device, noise=None):
+    return _noise_source(noise, device).rand(batch_size, seq_len, z_dim)
+
+
+# ---------------------- Losses (tt:70-126) ----------------------
+
+bce = _losses.bce
+recon_loss = _losses.recon_loss
+sup_loss = _losses.sup_loss
+sup_loss_fake = _losses.sup_loss_fake
+
+
+def acf_loss_torch(x_gen: torch.Tensor, x_real: torch.Tensor, max_lag: int) -> torch.Tensor:
+    return _losses.cov_acf_losses(x_gen, x_real, max_lag, need_cov=False, need_acf=True)[1]
+
+
+def _params(*modules):
+    out = []
+    for m in modules:
+        out += list(m.parameters())
+    return out
+
+
+def _zero_grads(opt):
+    opt.zero_grad(set_to_none=True)
+
+
+def _reduce_and_step(opt, params, clip):
+    """DP: SUM-all-reduce the local gradient contributions (dist.py), then clip_grad_norm_ + Adam."""
+    if _dist.is_enabled():
+        b = _dist.GradBuckets()
+        b.launch(params)
+        b.wait()
+    clip_and_step(opt, params, clip)
+
+
+def _as_float(t, sync):
+    return t.item() if sync else t.detach()
+
+
+# ---------------------- Training phases ----------------------
+
+def phase_autoencoder(model: TimeGAN, loader: DataLoader, device, optER: optim.Optimizer, clip: float, epochs: int,
+                      log):
+    """tt:131-144."""
+    model.train()
+    params = _params(model.embedder, model.recovery)
+    for ep in range(1, epochs + 1):
+        epoch_loss = torch.zeros((), device=device)
+        n = 0
+        for (x_batch,) in loader:
+            x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+            x_tilde = model.reconstruct(x)
+            loss = recon_loss(x, x_tilde)
+            _zero_grads(optER)
+            loss.backward()
+            _reduce_and_step(optER, params, clip)
+            epoch_loss += loss.detach() * x_batch.size(0)
+            n += x_batch.size(0)
+        log(f"[AE] epoch {ep}/{epochs}  recon={epoch_loss.item() / n:.5f}")
+
+
+def phase_supervisor(model: TimeGAN, loader: DataLoader, device, optS: optim.Optimizer, clip: float, epochs: int, log):
+    """tt:147-163."""
+    model.train()
+    params = _params(model.supervisor)
+    for ep in range(1, epochs + 1):
+        epoch_loss = torch.zeros((), device=device)
+        n = 0
+        for (x_batch,) in loader:
+            x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+            with torch.no_grad():
+                h = model.encode(x)
+            h_in, h_tgt = h[:, :-1, :].contiguous(), h[:, 1:, :].contiguous()
+            h_pred = model.supervisor(h_in)
+            loss = _losses.mse_loss(h_pred, h_tgt)
+            _zero_grads(optS)
+            loss.backward()
+            _reduce_and_step(optS, params, clip)
+            epoch_loss += loss.detach() * x_batch.size(0)
+            n += x_batch.size(0)
+        log(f"[SUP] epoch {ep}/{epochs}  sup={epoch_loss.item() / n:.5f}")
+
+
+def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, clip, schedulerD=None,
+              r1_gamma: float = 1.0, target_acc: float = 0.55, band: float = 0.10, *, noise=None, sync: bool = True):
+    """Discriminator update with R1 and the soft throttle (tt:166-225).  Returns (loss, acc)."""
+    D = model.discriminator
+    D.train()
+    nz = _noise_source(noise, device)
+    B, T = x.size(0), x.size(1)
+    gru = D.rnn.rnn
+    wd = [w.detach() for w in gru.layer_weights()]
+
+    with torch.no_grad():
+        h_real = model.encode(x)                                                     # tt:175-176
+        z = nz.rand(B, T, model.embedder.rnn.rnn.hidden_size)                        # tt:179
+        h_fake = model.refine_latent(model.gen_latent(z))                            # tt:180-181 (forward only)
+        h_real_n = add_instance_noise(h_real, inst_noise_std, nz, True)              # tt:184
+        h_fake_n = add_instance_noise(h_fake, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:185
+        y_real, y_fake = smooth_labels(B, label_smooth, device, nz)                  # tt:188
+        # one 2B-batch pass of the D stack over [real ; fake] (tt:191-193)
+        h_in = torch.cat([h_real_n, h_fake_n], 0)
+        masks = gru.dropout_masks(h_in)
+        y_all, saves = ops.stack_forward(h_in, wd, save=True, masks=masks)
+        last = y_all[:, -1, :]
+    yl_r = last[:B].clone().requires_grad_(True)
+    yl_f = last[B:].clone().requires_grad_(True)
+    wbar_r = D.sn_weight()                                                           # power iteration 1 (tt:192)
+    d_real = torch.sigmoid(torch.nn.functional.linear(yl_r, wbar_r, D.fc.bias))
+    d_fake = D.head(yl_f)                                                            # power iteration 2 (tt:193)
+
+    loss_bce = 0.5 * (bce(d_real, y_real) + bce(d_fake, y_fake))                    # tt:196
+    Bg = B * _dist.world_size()
+
+    r1 = None
+    obj = loss_bce
+    if r1_gamma > 0.0:                                                               # tt:199-202
+        saves_r = [sv.narrow(0, B) for sv in saves]
+        masks_r = None if masks is None else [m[:B] for m in masks]
+        seed = torch.autograd.grad(d_real.sum(), yl_r, retain_graph=True)[0]
+        with torch.no_grad():
+            v, _ = ops.stack_backward(seed, saves_r, wd, need_dx=True, need_dw=False, dy_last=True, masks=masks_r)
+            r1 = _dist.global_mean(_losses.sumsq(v), B)
+            ydot, tsaves = ops.stack_jvp_forward(v, saves_r, wd, masks=masks_r)
+        hd_last = ydot[:, -1, :].clone().requires_grad_(True)
+        sdot = (d_real * (1.0 - d_real) * torch.nn.functional.linear(hd_last, wbar_r)).sum()
+        obj = obj + (r1_gamma / Bg) * sdot          # d(0.5*gamma*r1)/dtheta = (gamma/B) d(sdot)/dtheta
+
+    with torch.no_grad():                                                            # tt:205-215
+        acc_real = _dist.global_mean((d_real > 0.5).float().sum(), B)
+        acc_fake = _dist.global_mean((d_fake < 0.5).float().sum(), B)
+        acc = 0.5 * (acc_real + acc_fake)
+        if band > 0:
+            scale = torch.clamp(1.0 - torch.clamp(acc - target_acc, min=0.0) / band, min=0.2)
+        else:
+            scale = torch.ones((), device=device)
+        loss_val = loss_bce.detach() + (0.5 * r1_gamma * r1 if r1 is not None else 0.0)
+        loss_val = loss_val * scale
+
+    head_params = [D.fc.weight_orig, D.fc.bias]
+    if r1 is not None:
+        gyr, gyf, ghd, gw, gb = torch.autograd.grad(obj * scale, [yl_r, yl_f, hd_last] + head_params)
+    else:
+        gyr, gyf, gw, gb = torch.autograd.grad(obj * scale, [yl_r, yl_f] + head_params)
+
+    with torch.no_grad():
+        grads = ops.alloc_like_flat(wd)
+        if r1 is not None:
+            saves_f = [sv.narrow(B, B) for sv in saves]
+            masks_f = None if masks is None else [m[B:] for m in masks]
+            ops.stack_backward(gyf, saves_f, wd, need_dx=False, need_dw=True, dy_last=True, grads=grads,
+                               accumulate=False, masks=masks_f)
+            ops.stack_jvp_backward(gyr, ghd, saves_r, tsaves, wd, grads, accumulate=True, masks=masks_r)
+        else:
+            ops.stack_backward(torch.cat([gyr, gyf], 0), saves, wd, need_dx=False, need_dw=True, dy_last=True,
+                               grads=grads, accumulate=False, masks=masks)
+    _zero_grads(optD)                                                                # tt:218-221
+    for p, g in zip(gru.layer_weights(), grads):
+        p.grad = g
+    D.fc.weight_orig.grad, D.fc.bias.grad = gw, gb
+    _reduce_and_step(optD, _params(D), clip)
+    if schedulerD is not None:
+        schedulerD.step()
+    return _as_float(loss_val, sync), _as_float(acc, sync)
+
+
+def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_std, clip, schedulerG=None,
+             gamma_cov: float = 0.0, gamma_acf: float = 0.0, acf_max_lag: int = 32, *, noise=None,
+             sync: bool = True):
+    """Generator/supervisor/embedder/recovery update (tt:228-276).  Returns the six logged losses."""
+    model.generator.train(); model.supervisor.train(); model.embedder.train(); model.recovery.train()
+    nz = _noise_source(noise, device)
+    B, T = x.size(0), x.size(1)
+
+    z = nz.rand(B, T, model.embedder.rnn.rnn.hidden_size)                            # tt:235
+    e_hat = model.gen_latent(z)
+    h_hat = model.refine_latent(e_hat)
+    d_fake = model.discriminator(add_instance_noise(h_hat, inst_noise_std, nz, _latent_is_gru_view(model)),
+                                 frozen=True)                                        # tt:240
+    g_adv = bce(d_fake, torch.ones_like(d_fake))
+    g_sup = sup_loss_fake(h_hat)                                                     # tt:244
+    x_tilde = model.reconstruct(x)                                                   # tt:247-248
+    g_rec = recon_loss(x, x_tilde)
+    x_hat = model.decode(h_hat)                                                      # tt:251
+
+    cov_term = torch.zeros((), device=device)
+    acf_term = torch.zeros((), device=device)
+    if gamma_cov > 0 or gamma_acf > 0:                                               # tt:254-263
+        cov_term, acf_term = _losses.cov_acf_losses(x_hat, x, acf_max_lag, need_cov=gamma_cov > 0,
+                                                    need_acf=gamma_acf > 0)
+    g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
+
+    _zero_grads(optG)
+    g_total.backward()
+    params = _params(model.generator, model.supervisor, model.embedder, model.recovery)
+    _reduce_and_step(optG, params, clip)
+    if schedulerG is not None:
+        schedulerG.step()
+    vals = (g_total, g_adv, g_sup, g_rec, cov_term, acf_term)
+    return tuple(_as_float(v, sync) for v in vals)
+
+
+# ---------------------- Full training (tt:281-422) ----------------------
+
+def train_single_npz(npz_path: Path, out_dir: Path,
+                     batch_size=64,
+                     ae_epochs=120,
+                     sup_epochs=150,
+                     gan_steps=8000,
+                     lr_g=1e-3, lr_d=2e-4,
+                     betas=(0.5, 0.9),
+                     alpha_sup=5.0,
+                     beta_rec=0.2,
+                     label_smooth=0.2,
+                     inst_noise_start=0.3,
+                     inst_noise_end=0.1,
+                     grad_clip=0.5,
+                     layers=1,
+                     dropout=0.2,
+                     seed=42,
+                     r1_gamma=1.0,
+                     d_min_acc=0.45,
+                     d_max_acc=0.60,
+                     gamma_cov=0.05,
+                     gamma_acf=0.05,
+                     acf_max_lag=64,
+                     device=None,
+                     *,
+                     z_dim: Optional[int] = None,
+                     hidden_dim: Optional[int] = None,
+                     noise: Optional[str] = None,
+                     proj_dtype: str = "fp32",
+                     log_every: int = 1):
+    """Same schedule, logs and artefacts as the reference.  Extras (keyword-only): `z_dim`/`hidden_dim`
+    override adaptive_dims; `noise="host"` replays the reference's CPU random stream (parity runs), default is
+    on-device Philox; `proj_dtype` "fp32" | "bf16" (tensor-core input projections); `log_every` k > 1 keeps
+    the per-step scalars on the device and flushes CSV rows / best-checkpoint decisions every k steps."""
+    npz_path, out_dir = Path(npz_path), Path(out_dir)
+    set_seeds(seed)
+    device = device or device_autoselect()
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("timegan_b200.train_single_npz: device must be CUDA; there is no CPU path")
+    rank0 = _dist.rank() == 0
+    out_dir.mkdir(parents=True, exist_ok=True)
+    ops.set_proj_mode(proj_dtype)
+
+    data = np.load(npz_path)
+    X = data["X"].astype(np.float32)
+    N, T, C = X.shape
+    zd, hd = adaptive_dims(C, T)
+    z_dim = int(z_dim) if z_dim is not None else zd
+    h_dim = int(hidden_dim) if hidden_dim is not None else hd
+
+    log_file = out_dir / "train_log.csv"
+    if rank0:
+        with open(log_file, "w", newline="") as f:
+            csv.writer(f).writerow(["step", "phase", "loss_D", "acc_D", "loss_G", "loss_adv", "loss_sup", "loss_rec",
+                                    "loss_cov", "loss_acf"])
+
+    def LOG(msg):
+        if rank0:
+            print(msg, flush=True)
+
+    LOG(f"==> {npz_path.name} | N={N} T={T} C={C}  z_dim={z_dim} h_dim={h_dim}  device={device}")
+
+    loader = make_loader(X, batch_size)
+    model = TimeGAN(x_dim=C, z_dim=z_dim, hidden_dim=h_dim, num_layers=layers, dropout=dropout).to(device)
+    nz = HostReplayNoise(device) if noise == "host" else None
+
+    optER = FusedAdam(_params(model.embedder, model.recovery), lr=lr_g, betas=betas)
+    phase_autoencoder(model, loader, device, optER, grad_clip, ae_epochs, LOG)
+
+    optS = FusedAdam(model.supervisor.parameters(), lr=lr_g, betas=betas)
+    phase_supervisor(model, loader, device, optS, grad_clip, sup_epochs, LOG)
+
+    optD = FusedAdam(model.discriminator.parameters(), lr=lr_d, betas=betas)
+    optG = FusedAdam(_params(model.generator, model.supervisor, model.embedder, model.recovery), lr=lr_g, betas=betas)
+    milestones = [gan_steps // 2, int(gan_steps * 0.75)]
+    schedulerG = optim.lr_scheduler.MultiStepLR(optG, milestones=milestones, gamma=0.5)
+    schedulerD = optim.lr_scheduler.MultiStepLR(optD, milestones=milestones, gamma=0.5)
+
+    loader_iter = iter(loader)
+    inst_noise = inst_noise_start
+    noise_decay = (inst_noise_start - inst_noise_end) / max(1, gan_steps)
+    best_ckpt_loss = math.inf
+    ckpt_path, best_path = out_dir / "ckpt_latest.pt", out_dir / "ckpt_best.pt"
+    meta = {"npz": npz_path.name, "z_dim": z_dim, "h_dim": h_dim}
+    target = 0.5 * (d_min_acc + d_max_acc)
+    band = max(0.0, d_max_acc - d_min_acc)
+    pending = []   # (step, device scalars) awaiting a flush
+
+    def flush():
+        nonlocal best_ckpt_loss
+        if not pending:
+            return
+        vals = torch.stack([torch.stack([v.float().reshape(()) for v in row]) for _, row in pending]).cpu().tolist()
+        rows = []
+        for (st, _), r in zip(pending, vals):
+            rows.append([st, "GAN"] + r)
+            if st % 100 == 0:
+                LOG(f"[GAN] step {st}/{gan_steps}  D:loss={r[0]:.4f} acc≈{r[1]:.2f}  G:total={r[2]:.4f} "
+                    f"(adv={r[3]:.4f}, sup={r[4]:.4f}, rec={r[5]:.4f}, cov={r[6]:.4f}, acf={r[7]:.4f})")
+        if rank0:
+            with open(log_file, "a", newline="") as f:
+                csv.writer(f).writerows(rows)
+        last_step, last = rows[-1][0], rows[-1]
+        # best checkpoint (tt:410-413): with log_every == 1 this is the reference's per-step rule; with k > 1
+        # the current weights are saved when the LAST step of the window improved on the best seen so far.
+        if last[4] < best_ckpt_loss and rank0:
+            save_ckpt(best_path, model, optG, optD, last_step, dict(meta, best=True))
+        best_ckpt_loss = min([best_ckpt_loss] + [r[4] for r in rows])
+        pending.clear()
+
+    for step in range(1, gan_steps + 1):
+        try:
+            (x_batch,) = next(loader_iter)
+        except StopIteration:
+            loader_iter = iter(loader)
+            (x_batch,) = next(loader_iter)
+        x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+
+        d_loss, d_acc = disc_step(model, x, device, optD, label_smooth, inst_noise, grad_clip, schedulerD, r1_gamma,
+                                  target_acc=target, band=band, noise=nz, sync=False)
+        g_vals = gen_step(model, x, device, optG, alpha_sup, beta_rec, inst_noise, grad_clip, schedulerG, gamma_cov,
+                          gamma_acf, acf_max_lag, noise=nz, sync=False)
+        pending.append((step, (d_loss, d_acc) + tuple(g_vals)))
+        if len(pending) >= max(1, log_every) or step == gan_steps:
+            flush()
+
+        inst_noise = max(inst_noise_end, inst_noise - noise_decay)
+        if (step % 500 == 0 or step == gan_steps) and rank0:
+            flush()
+            save_ckpt(ckpt_path, model, optG, optD, step, meta)
+
+    model.eval()
+    from .generate_long_synth import generate_windows
+    X_hat = generate_windows(model, N, T, z_dim, device, noise=nz)
+    if rank0:
+        np.savez_compressed(out_dir / "synthetic.npz", X=X_hat)
+        print(f"Saved synthetic: {out_dir / 'synthetic.npz'}")
+    return True
+
+
+# ---------------------- Entry point (tt:427-495) ----------------------
+
+def build_argparser():
+    import argparse
+    ap = argparse.ArgumentParser(formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    ap.add_argument("--data_dir", type=str, default="./preprocessed",
+                    help="Folder with postureX_with_exo.npz / postureX_no_exo.npz")
+    ap.add_argument("--out_dir", type=str, default="./timegan_runs", help="Output root folder")
+    ap.add_argument("--batch_size", type=int, default=64)
+    ap.add_argument("--ae_epochs", type=int, default=120)
+    ap.add_argument("--sup_epochs", type=int, default=150)
+    ap.add_argument("--gan_steps", type=int, default=8000)
+    ap.add_argument("--lr_g", type=float, default=1e-3)
+    ap.add_argument("--lr_d", type=float, default=2e-4)
+    ap.add_argument("--beta1", type=float, default=0.5)
+    ap.add_argument("--beta2", type=float, default=0.9)
+    ap.add_argument("--alpha_sup", type=float, default=5.0)
+    ap.add_argument("--beta_rec", type=float, default=0.2)
+    ap.add_argument("--label_smooth", type=float, default=0.2)
+    ap.add_argument("--inst_noise_start", type=float, default=0.3)
+    ap.add_argument("--inst_noise_end", type=float, default=0.1)
+    ap.add_argument("--grad_clip", type=float, default=0.5)
+    ap.add_argument("--layers", type=int, default=1)
+    ap.add_argument("--dropout", type=float, default=0.2)
+    ap.add_argument("--seed", type=int, default=42)
+    ap.add_argument("--r1_gamma", type=float, default=1.0)
+    ap.add_argument("--d_min_acc", type=float, default=0.45)
+    ap.add_argument("--d_max_acc", type=float, default=0.60)
+    ap.add_argument("--gamma_cov", type=float, default=0.05)
+    ap.add_argument("--gamma_acf", type=float, default=0.05)
+    ap.add_argument("--acf_max_lag", type=int, default=64)
+    # extras of this implementation (defaults = reference behaviour)
+    ap.add_argument("--z_dim", type=int, default=None, help="override adaptive_dims' latent size")
+    ap.add_argument("--hidden_dim", type=int, default=None, help="override adaptive_dims' hidden size")
+    ap.add_argument("--proj_dtype", type=str, default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--noise", type=str, default=None, choices=[None, "host"])
+    ap.add_argument("--log_every", type=int, default=1)
+    return ap
+
+
+def main(argv=None):
+    args = build_argparser().parse_args(argv)
+    _dist.init()
+    device = device_autoselect()
+    print(f"Using device: {device}")
+    out_root = Path(args.out_dir)
+    out_root.mkdir(parents=True, exist_ok=True)
+    files = sorted(Path(args.data_dir).glob("posture*_*.npz"))
+    if not files:
+        raise SystemExit(f"No NPZs found in {args.data_dir}. Run preprocessing first.")
+    for fp in files:
+        train_single_npz(
+            fp, out_root / fp.stem,
+            batch_size=args.batch_size, ae_epochs=args.ae_epochs, sup_epochs=args.sup_epochs,
+            gan_steps=args.gan_steps, lr_g=args.lr_g, lr_d=args.lr_d, betas=(args.beta1, args.beta2),
+            alpha_sup=args.alpha_sup, beta_rec=args.beta_rec, label_smooth=args.label_smooth,
+            inst_noise_start=args.inst_noise_start, inst_noise_end=args.inst_noise_end, grad_clip=args.grad_clip,
+            layers=args.layers, dropout=args.dropout, seed=args.seed, r1_gamma=args.r1_gamma,
+            d_min_acc=args.d_min_acc, d_max_acc=args.d_max_acc, gamma_cov=args.gamma_cov, gamma_acf=args.gamma_acf,
+            acf_max_lag=args.acf_max_lag, device=device, z_dim=args.z_dim, hidden_dim=args.hidden_dim,
+            proj_dtype=args.proj_dtype, noise=args.noise, log_every=args.log_every)
+
+
+if __name__ == "__main__":
+    main()
