@@ -1,0 +1,328 @@
+#!/usr/bin/env python3
+"""bench.py -- TimeGAN joint-training throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--hidden H] [--batch B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N ...
+
+A "step" is ONE joint training step (disc_step + gen_step, train_timegan.py:379-395) over one batch of
+synthetic (B,768,14) windows.  Workload at every N: BASELINE config c2 per GPU -- z = hidden = 64, 3-layer GRU
+stacks, batch 256 per GPU, fp32 (weak scaling: global batch = 256 N, gradients all-reduced over NCCL).
+
+One JSON line on rank 0:
+  value        sequences/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e          the same step driven from HOST buffers: pinned-host batch -> H2D copy -> disc_step/gen_step ->
+               D2H read of the 8 logged loss scalars, all inside the timed region
+  roofline     dominant kernel family of the step (device time share), its algorithmic bytes / launch duration
+               against the measured HBM copy bandwidth; `ffma` gives the same family against the fp32 FMA peak
+  cpu_baseline oracle/timegan_ref.py (the CPU restatement of the reference; kind "port") on this box's host cores,
+               on a bounded sample of the same workload
+  --impl reference : only the CPU leg, K timed steps of that bounded sample (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+T_LEN, X_DIM = 768, 14
+HP = dict(label_smooth=0.2, inst_noise=0.3, clip=0.5, r1_gamma=1.0, target=0.525, band=0.15, alpha_sup=5.0,
+          beta_rec=0.2, gamma_cov=0.05, gamma_acf=0.05, acf_max_lag=64, lr_g=1e-3, lr_d=2e-4, betas=(0.5, 0.9))
+METRIC = "TimeGAN train seq/sec (T=768,C=14)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hidden", type=int, default=64)
+    ap.add_argument("--layers", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
+    ap.add_argument("--proj", type=str, default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    cfg = "c2" if (a.hidden, a.layers, a.batch) == (64, 3, 256) else "custom"
+    return (f"{cfg}: TimeGAN joint step (disc_step+gen_step) z=h={a.hidden} L={a.layers} B={a.batch}/GPU "
+            f"T={T_LEN} C={X_DIM} {a.proj} projections")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: oracle port of the reference on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+def cpu_joint_steps(a, steps, warmup, threads):
+    """Times `steps` joint steps of the oracle port on a (B, t_s, 14) sample and rescales to T=768.
+
+    The sample keeps the FULL batch (per-sequence CPU cost depends on B through ATen dispatch amortisation) and
+    shortens the window to t_s timesteps; the recurrence costs the same per timestep, so a T=768 step costs
+    768/t_s times the sample (the T-independent parts -- optimiser, head -- are <1 % of a CPU step)."""
+    import torch
+    from oracle import timegan_ref as R
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    ts = min(a.cpu_sample_t, T_LEN)
+    model = R.build_model(X_DIM, a.hidden, a.hidden, a.layers, 0.0)
+    opts = R.make_optimizers(model, HP["lr_g"], HP["lr_d"], HP["betas"])
+    x = torch.rand(a.batch, ts, X_DIM)
+    nz = R.TorchNoise()
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        R.d_step(model, x, opts["D"], nz, HP["label_smooth"], HP["inst_noise"], HP["clip"], HP["r1_gamma"],
+                 HP["target"], HP["band"])
+        R.g_step(model, x, opts["G"], nz, HP["alpha_sup"], HP["beta_rec"], HP["inst_noise"], HP["clip"],
+                 HP["gamma_cov"], HP["gamma_acf"], HP["acf_max_lag"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    scale = T_LEN / ts
+    per_step = sum(times) / len(times) * scale
+    return a.batch / per_step, per_step, ts
+
+
+def cpu_baseline(a):
+    import torch
+    cores = os.cpu_count() or 1
+    best = None
+    for th in sorted({1, min(cores, 8), cores}):
+        try:
+            v, per_step, ts = cpu_joint_steps(a, 1, 0, th)
+        except Exception as e:  # pragma: no cover
+            print(f"[bench] cpu baseline with {th} threads failed: {e}", file=sys.stderr)
+            continue
+        if best is None or v > best[0]:
+            best = (v, th, per_step, ts)
+    v, th, per_step, ts = best
+    return {"value": round(v, 4), "unit": "seq/s", "cores": th, "kind": "port", "host_cores": cores,
+            "sample": f"1 joint step of oracle/timegan_ref.py (torch {torch.__version__}, CPU) on the full batch "
+                      f"{a.batch} x first {ts} of {T_LEN} timesteps, time scaled x{T_LEN / ts:g} "
+                      f"(recurrence is linear in T); best of {{1, 8, all}} threads",
+            "s_per_step_full_T": round(per_step, 3)}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # pick the thread count that is fastest on this host from one un-timed probe each
+    probe = {}
+    for th in sorted({1, min(cores, 8), cores}):
+        probe[th] = cpu_joint_steps(a, 1, 0, th)[0]
+    th = max(probe, key=probe.get)
+    steps = max(1, a.steps)
+    # size the sample so that `steps` timed CPU steps take about 150 s on this host
+    sample_s = a.batch / probe[th] * a.cpu_sample_t / T_LEN       # seconds per sampled step at cpu_sample_t
+    if steps * sample_s > 150.0:
+        a.cpu_sample_t = max(16, int(a.cpu_sample_t * 150.0 / (steps * sample_s)) // 8 * 8)
+    v, per_step, ts = cpu_joint_steps(a, steps, min(a.warmup, 1), th)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "seq/s", "n_gpus": a.gpus, "steps": steps,
+        "warmup": a.warmup, "ms_per_step": round(per_step * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "device": "host CPU"},
+        "cpu_baseline": {"value": round(v, 4), "unit": "seq/s", "cores": th, "kind": "port", "host_cores": cores,
+                         "sample": f"each step = 1 joint step of oracle/timegan_ref.py on the full batch {a.batch} x "
+                                   f"first {ts} of {T_LEN} timesteps, time scaled x{T_LEN / ts:g}; thread count "
+                                   f"chosen from probes {probe}"},
+        "e2e": {"value": round(v, 4), "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md: sample DURING the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.th = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.th = threading.Thread(target=self._read, daemon=True)
+        self.th.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU leg
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as td
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the TimeGAN hot path only exists as sm_100a kernels")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import timegan_b200 as tg
+    from timegan_b200 import _lib, ops, dist as tdist, train_timegan as tt
+    if world > 1:
+        tdist.init(backend="nccl", device=dev)
+    ops.set_proj_mode(a.proj)
+
+    torch.manual_seed(42)
+    model = tg.TimeGAN(X_DIM, a.hidden, a.hidden, a.layers, 0.0).to(dev)
+    P = tt._params
+    optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"])
+    optG = tg.FusedAdam(P(model.generator, model.supervisor, model.embedder, model.recovery), lr=HP["lr_g"],
+                        betas=HP["betas"])
+    B = a.batch
+    n_batches = 8
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = [torch.rand(B, T_LEN, X_DIM, generator=g).pin_memory() for _ in range(n_batches)]
+    resident = [h.to(dev) for h in host]
+
+    def joint(x):
+        d = tt.disc_step(model, x, dev, optD, HP["label_smooth"], HP["inst_noise"], HP["clip"], None, HP["r1_gamma"],
+                         target_acc=HP["target"], band=HP["band"], sync=False)
+        gq = tt.gen_step(model, x, dev, optG, HP["alpha_sup"], HP["beta_rec"], HP["inst_noise"], HP["clip"], None,
+                         HP["gamma_cov"], HP["gamma_acf"], HP["acf_max_lag"], sync=False)
+        return d + gq
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        return float(t.item())
+
+    for i in range(max(a.warmup, 3)):
+        joint(resident[i % n_batches])
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM ----
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    _lib.prof_reset()
+    _lib.prof_enable(True)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        out = joint(resident[i % n_batches])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = _lib.launch_count() - l0
+    _lib.prof_enable(False)
+    prof = _lib.prof_read()
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- timed region 2: end to end from host buffers ----
+    scal = torch.empty(8, dtype=torch.float32).pin_memory()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(a.steps):
+        x = host[i % n_batches].to(dev, non_blocking=True)
+        out = joint(x)
+        scal.copy_(torch.stack([o.float().reshape(()) for o in out]), non_blocking=False)
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    assert all(v == v for v in scal.tolist()), f"non-finite losses in bench: {scal.tolist()}"
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    total_dev_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    dom = max(prof, key=lambda k: prof[k]["ms"])
+    d = prof[dom]
+    ach_gbs = d["bytes"] / (d["ms"] * 1e-3) / 1e9 if d["ms"] > 0 else 0.0
+    sm_mhz = (clk or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    ffma_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    ach_tf = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+    seqs = B * world * a.steps
+    line = {
+        "metric": METRIC, "value": round(seqs / (ms * 1e-3), 2), "unit": "seq/s", "n_gpus": world, "steps": a.steps,
+        "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if a.proj == "fp32" else "fp32 (bf16 projections)",
+        "data": "synthetic",
+        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
+                   "l2": f"{n_batches} rotating input batches; each step streams >2 GB of activations (>> 126 MB L2)"},
+        "e2e": {"value": round(seqs / (ms_e2e * 1e-3), 2), "unit": "seq/s",
+                "h2d_bytes_per_step": B * T_LEN * X_DIM * 4, "d2h_bytes_per_step": 8 * 4,
+                "ms_per_step": round(ms_e2e / a.steps, 3)},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
+                     "frac": round(ach_gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                     "avg_launch_ms": round(d["ms"] / max(d["calls"], 1), 4), "launches": d["calls"],
+                     "share_of_device_time": round(d["ms"] / total_dev_ms, 4),
+                     "ffma": {"achieved": round(ach_tf, 2), "peak": round(ffma_peak, 1), "unit": "TFLOP/s",
+                              "frac": round(ach_tf / ffma_peak, 4),
+                              "note": "W_hh h runs on fp32 FMA pipes by design; peak = 148 SM x 128 FMA x 2 x sampled clock"}},
+        "families": {k: {"ms_per_step": round(v["ms"] / a.steps, 3), "calls_per_step": round(v["calls"] / a.steps, 1),
+                         "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
+                         "TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else 0.0}
+                     for k, v in prof.items() if v["calls"]},
+    }
+    if not a.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline(a)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

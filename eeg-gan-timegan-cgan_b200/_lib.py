@@ -31,6 +31,12 @@ SIGNATURES = {
     "tg_version": (_i, []),
     "tg_last_error": (C.c_char_p, []),
     "tg_device_sm_count": (_i, []),
+    "tg_launch_count": (_ll, []),
+    "tg_prof_kinds": (_i, []),
+    "tg_prof_kind_name": (C.c_char_p, [_i]),
+    "tg_prof_enable": (None, [_i]),
+    "tg_prof_reset": (None, []),
+    "tg_prof_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tg_proj": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i]),
     "tg_dgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i]),
     "tg_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -74,6 +80,28 @@ def check(rc: int, what: str = ""):
     if rc != 0:
         kind = "argument error" if rc < 0 else "CUDA error"
         raise RuntimeError(f"libtimegan_b200 {what}: {kind} {rc}: {last_error()}")
+
+
+def launch_count() -> int:
+    return int(lib.tg_launch_count())
+
+
+def prof_enable(on: bool):
+    lib.tg_prof_enable(1 if on else 0)
+
+
+def prof_reset():
+    lib.tg_prof_reset()
+
+
+def prof_read() -> dict:
+    """{family: {"ms", "calls", "bytes", "flops"}} since the last prof_reset (synchronises the recorded events)."""
+    out = {}
+    for k in range(lib.tg_prof_kinds()):
+        ms, calls, by, fl = C.c_double(), _ll(), C.c_double(), C.c_double()
+        check(lib.tg_prof_read(k, C.byref(ms), C.byref(calls), C.byref(by), C.byref(fl)), "tg_prof_read")
+        out[lib.tg_prof_kind_name(k).decode()] = dict(ms=ms.value, calls=calls.value, bytes=by.value, flops=fl.value)
+    return out
 
 
 def stream_ptr() -> int:

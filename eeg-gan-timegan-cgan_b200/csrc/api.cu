@@ -3,8 +3,10 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "losses.h"
+#include <atomic>
 #include <mutex>
 #include <string.h>
+#include <vector>
 
 static thread_local char g_err[512] = "";
 
@@ -15,7 +17,49 @@ void tg_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// ---- launch accounting + optional per-family CUDA-event profiling (bench.py's roofline numbers) -------------
+// Every kernel launch goes through tg_check_launch, which counts it.  With profiling enabled each C-ABI call
+// is bracketed by a cudaEvent pair on ITS stream; tg_prof_read sums the elapsed times per kernel family
+// together with the algorithmic bytes / FLOPs the calls declared.  Disabled (the default) it costs nothing.
+namespace {
+enum { K_GRU_FWD = 0, K_GRU_BWD, K_JVP_FWD, K_JVP_BWD, K_PROJ, K_DGRAD, K_WGRAD, K_LOSS, K_OPTIM, K_RNG, K_COUNT };
+const char* const kKindNames[K_COUNT] = {"gru_fwd", "gru_bwd", "gru_jvp_fwd", "gru_jvp_bwd", "proj",
+                                         "dgrad",   "wgrad",   "loss",        "optim",       "rng"};
+struct ProfRec { cudaEvent_t a, b; int kind; };
+std::mutex g_prof_mu;
+std::atomic<long long> g_launches{0};
+bool g_prof_on = false;
+std::vector<ProfRec> g_recs;          // recorded pairs of the current session
+std::vector<ProfRec> g_pool;          // reusable events
+double g_bytes[K_COUNT], g_flops[K_COUNT];
+long long g_calls[K_COUNT];
+constexpr size_t kMaxRecs = 1 << 17;
+
+struct ProfScope {
+  cudaStream_t st; int idx = -1;
+  ProfScope(void* stream, int kind, double bytes, double flops) : st((cudaStream_t)stream) {
+    if (!g_prof_on) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_bytes[kind] += bytes; g_flops[kind] += flops; g_calls[kind] += 1;
+    if (g_recs.size() >= kMaxRecs) return;
+    ProfRec r;
+    if (!g_pool.empty()) { r = g_pool.back(); g_pool.pop_back(); }
+    else if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    r.kind = kind;
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+    idx = (int)g_recs.size() - 1;
+  }
+  ~ProfScope() {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_recs[idx].b, st);
+  }
+};
+}  // namespace
+
 int tg_check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     tg_set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -45,8 +89,41 @@ int tg_version(void) { return TG_ABI_VERSION; }
 const char* tg_last_error(void) { return g_err; }
 int tg_device_sm_count(void) { return tg_num_sms(); }
 
+long long tg_launch_count(void) { return g_launches.load(); }
+int tg_prof_kinds(void) { return K_COUNT; }
+const char* tg_prof_kind_name(int kind) { return (kind >= 0 && kind < K_COUNT) ? kKindNames[kind] : ""; }
+void tg_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+}
+void tg_prof_reset(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_recs) g_pool.push_back(r);
+  g_recs.clear();
+  for (int k = 0; k < K_COUNT; ++k) { g_bytes[k] = g_flops[k] = 0.0; g_calls[k] = 0; }
+}
+int tg_prof_read(int kind, double* ms, long long* calls, double* bytes, double* flops) {
+  if (kind < 0 || kind >= K_COUNT) { tg_set_error("prof_read: bad kind %d", kind); return TG_ERR_ARG; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double total = 0.0;
+  for (auto& r : g_recs) {
+    if (r.kind != kind) continue;
+    cudaError_t e = cudaEventSynchronize(r.b);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.a, r.b);
+    if (e != cudaSuccess) { tg_set_error("prof_read: %s", cudaGetErrorString(e)); return (int)e; }
+    total += t;
+  }
+  if (ms) *ms = total;
+  if (calls) *calls = g_calls[kind];
+  if (bytes) *bytes = g_bytes[kind];
+  if (flops) *flops = g_flops[kind];
+  return TG_OK;
+}
+
 int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
             int M, int N, int K, int accumulate, int mode) {
+  ProfScope _ps(stream, K_PROJ, 4.0 * ((double)M * K + (double)N * K + (double)M * N), 2.0 * M * N * K);
   if (mode == TG_PROJ_BF16) {
     int rc = tg_proj_tc_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
     if (rc != TG_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core tile cannot take run exact fp32
@@ -56,6 +133,7 @@ int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, cons
 
 int tg_dgrad(void* stream, const float* dG, int ldg, const float* W, int ldw, float* dX, int ldx, int M, int N, int K,
              int accumulate) {
+  ProfScope _ps(stream, K_DGRAD, 4.0 * ((double)M * K + (double)N * K + (double)M * N), 2.0 * M * N * K);
   return tg_gemm_nn_impl((cudaStream_t)stream, dG, ldg, W, ldw, dX, ldx, M, N, K, accumulate);
 }
 
@@ -63,85 +141,103 @@ size_t tg_wgrad_workspace_bytes(int M, int N, int K) { return tg_wgrad_ws_bytes(
 
 int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
              int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes) {
+  ProfScope _ps(stream, K_WGRAD, 4.0 * ((double)M * N + (double)M * K + (double)N * K), 2.0 * M * N * K);
   return tg_wgrad_impl((cudaStream_t)stream, dG, ldg, A, lda, dW, lddw, db, M, N, K, a_shift_T, accumulate, (float*)ws,
                        ws_bytes);
 }
 
 int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, float* y, float* q, int B, int T, int H,
                int flags) {
+  ProfScope _ps(stream, K_GRU_FWD, (double)B * T * H * ((flags & TG_GRU_SAVE) ? 32.0 : 16.0), 6.0 * B * T * (double)H * H);
   return tg_gru_fwd_impl((cudaStream_t)stream, gi, w_hh, b_hh, y, q, B, T, H, flags);
 }
 
 int tg_gru_bwd(void* stream, const float* dy, const float* rzn, const float* q, const float* y, const float* w_hh,
                float* dgi, float* dq, int B, int T, int H, int flags) {
+  ProfScope _ps(stream, K_GRU_BWD, (double)B * T * H * ((flags & TG_GRU_DY_LAST) ? 36.0 : 40.0), 6.0 * B * T * (double)H * H);
   return tg_gru_bwd_impl((cudaStream_t)stream, dy, rzn, q, y, w_hh, dgi, dq, B, T, H, flags);
 }
 
 int tg_gru_jvp_fwd(void* stream, float* gid, const float* rzn, const float* q, const float* y, const float* w_hh,
                    float* ydot, float* qdot, int B, int T, int H, int flags) {
+  ProfScope _ps(stream, K_JVP_FWD, (double)B * T * H * 56.0, 6.0 * B * T * (double)H * H);
   return tg_gru_jvp_fwd_impl((cudaStream_t)stream, gid, rzn, q, y, w_hh, ydot, qdot, B, T, H, flags);
 }
 
 int tg_gru_jvp_bwd(void* stream, const float* hbar, const float* hdbar, const float* rzn, const float* q,
                    const float* ta, const float* qdot, const float* y, const float* ydot, const float* w_hh,
                    float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags) {
+  ProfScope _ps(stream, K_JVP_BWD, (double)B * T * H * 104.0, 12.0 * B * T * (double)H * H);
   return tg_gru_jvp_bwd_impl((cudaStream_t)stream, hbar, hdbar, rzn, q, ta, qdot, y, ydot, w_hh, gib, qb, gidb, qdb, B,
                              T, H, flags);
 }
 
 size_t tg_reduce_workspace_bytes(void) { return tg_reduce_ws_bytes(); }
 int tg_sqdiff_sum(void* stream, const float* a, const float* b, long long n, float* out, void* ws, size_t ws_bytes) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_sqdiff_sum_impl((cudaStream_t)stream, a, b, n, out, ws, ws_bytes);
 }
 int tg_scaled_diff(void* stream, const float* a, const float* b, const float* coef, float* out, long long n,
                    int accumulate) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_scaled_diff_impl((cudaStream_t)stream, a, b, coef, out, n, accumulate);
 }
 int tg_diff1_sum(void* stream, const float* h, int B, int T, int H, float* out, void* ws, size_t ws_bytes) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_diff1_sum_impl((cudaStream_t)stream, h, B, T, H, out, ws, ws_bytes);
 }
 int tg_diff1_grad(void* stream, const float* h, const float* coef, float* out, int B, int T, int H, int accumulate) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_diff1_grad_impl((cudaStream_t)stream, h, coef, out, B, T, H, accumulate);
 }
 int tg_center_scale(void* stream, const float* x, const float* mean, const float* scale, float* out, long long rows,
                     int C) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_center_scale_impl((cudaStream_t)stream, x, mean, scale, out, rows, C);
 }
 int tg_acf_fwd(void* stream, const float* xz, int B, int T, int C, int L, float* part) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_acf_fwd_impl((cudaStream_t)stream, xz, B, T, C, L, part);
 }
 int tg_acf_bwd(void* stream, const float* xz, const float* S, int B, int T, int C, int L, float* gz, float* stat) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_acf_bwd_impl((cudaStream_t)stream, xz, S, B, T, C, L, gz, stat);
 }
 int tg_acf_bwd_final(void* stream, const float* gz, const float* xz, const float* mean_gz, const float* kc,
                      const float* inv_s, float* dx, long long rows, int C, int accumulate) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_acf_bwd_final_impl((cudaStream_t)stream, gz, xz, mean_gz, kc, inv_s, dx, rows, C, accumulate);
 }
 
 size_t tg_colsum_workspace_bytes(int N) { return tg_colsum_ws_bytes(N); }
 int tg_colsum(void* stream, const float* X, int ld, int M, int N, float* out, int accumulate, void* ws,
               size_t ws_bytes) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
   return tg_colsum_impl((cudaStream_t)stream, X, ld, M, N, out, accumulate, (float*)ws, ws_bytes);
 }
 
 size_t tg_sumsq_workspace_bytes(int n, const long long* sizes) { return tg_sumsq_ws_bytes(n, sizes); }
 int tg_sumsq(void* stream, int n, const float* const* grads, const long long* sizes, float* out_sumsq, void* ws,
              size_t ws_bytes) {
+  ProfScope _ps(stream, K_OPTIM, 0.0, 0.0);
   return tg_sumsq_multi_impl((cudaStream_t)stream, n, grads, sizes, out_sumsq, ws, ws_bytes);
 }
 int tg_adam(void* stream, int n, float* const* params, const float* const* grads, float* const* exp_avg,
             float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr, float beta1,
             float beta2, float eps, int step, float grad_scale) {
+  ProfScope _ps(stream, K_OPTIM, 0.0, 0.0);
   return tg_adam_multi_impl((cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, sizes, sumsq, max_norm, lr,
                             beta1, beta2, eps, step, grad_scale);
 }
 
 int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,
                    float hi) {
+  ProfScope _ps(stream, K_RNG, 4.0 * (double)n, 0.0);
   return tg_rng_uniform_impl((cudaStream_t)stream, out, n, seed, offset, lo, hi);
 }
 int tg_rng_add_normal(void* stream, const float* in, float* out, long long n, float std, unsigned long long seed,
                       unsigned long long offset) {
+  ProfScope _ps(stream, K_RNG, 8.0 * (double)n, 0.0);
   return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, std, seed, offset);
 }
 

@@ -44,6 +44,18 @@ int tg_version(void);
 const char* tg_last_error(void);
 int tg_device_sm_count(void);
 
+/* ---- launch accounting and per-family device timing (measurement only; used by bench.py) -------------------
+ * tg_launch_count: kernels launched by this library since load.  With tg_prof_enable(1) every call below is
+ * bracketed by a cudaEvent pair on its own stream; tg_prof_read(kind) synchronises those events and returns
+ * the summed elapsed ms, the number of calls and the algorithmic bytes / FLOPs they declared since the last
+ * tg_prof_reset().  Kinds 0..tg_prof_kinds()-1 are named by tg_prof_kind_name(). */
+long long tg_launch_count(void);
+int tg_prof_kinds(void);
+const char* tg_prof_kind_name(int kind);
+void tg_prof_enable(int on);
+void tg_prof_reset(void);
+int tg_prof_read(int kind, double* ms, long long* calls, double* bytes, double* flops);
+
 /* ---- GRU layer, time-batched input projection:  C[M,N] (+)= A[M,K] W[N,K]^T + bias[N] -------------------
  * Replaces `params.linear_ih(input)` inside at::gru reached from timegan_model.py:33 (GRUStack.forward),
  * and the head Linears timegan_model.py:53 (Recovery.out), :66 (Generator.proj), :79 (Supervisor.proj).
