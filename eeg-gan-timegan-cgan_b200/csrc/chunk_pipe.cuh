@@ -24,24 +24,34 @@ struct ChunkPipe {
   int mode[NS];
   int shift[NS];
   int off[NS];
+  int bstride[NS];  // floats between consecutive sequences of one array inside a stage (padded, see seq_stride)
   int stage_floats;
   float* stages;
   uint64_t* full;
   int T, nb, b0, NC;
   bool reverse, bulk;
 
+  // Sequence b of an array starts seq_stride() floats after sequence b-1.  The pad makes the stride == 16
+  // (mod 32) so that the lanes of a warp that work on two different sequences (same hidden unit) hit
+  // different shared-memory banks, and keeps every row 16-B aligned for the bulk copies (pad % 4 == 0
+  // whenever TC*w % 4 == 0).
+  static __host__ __device__ __forceinline__ int seq_stride(int width) {
+    const int n = TC * width;
+    return (BT > 1) ? n + ((16 - (n % 32)) + 32) % 32 : n;
+  }
   __device__ __forceinline__ void layout() {
     int o = 0;
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
       off[k] = o;
-      o += BT * TC * w[k];
+      bstride[k] = seq_stride(w[k]);
+      o += BT * bstride[k];
     }
     stage_floats = o;
   }
   static __host__ __device__ int stage_floats_for(const int* widths) {
     int o = 0;
-    for (int k = 0; k < NS; ++k) o += BT * TC * widths[k];
+    for (int k = 0; k < NS; ++k) o += BT * seq_stride(widths[k]);
     return o;
   }
   __device__ __forceinline__ int t0_of(int c) const { return (reverse ? (NC - 1 - c) : c) * TC; }
@@ -50,7 +60,7 @@ struct ChunkPipe {
     return min(TC, T - t0);
   }
   __device__ __forceinline__ float* row(int s, int k, int b, int tl) const {
-    return stages + (size_t)s * stage_floats + off[k] + (b * TC + tl) * w[k];
+    return stages + (size_t)s * stage_floats + off[k] + b * bstride[k] + tl * w[k];
   }
 
   // ---- producer side (bulk mode: one thread) ------------------------------------------------

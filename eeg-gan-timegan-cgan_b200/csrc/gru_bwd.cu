@@ -5,10 +5,11 @@
 // math of SURVEY.md Appendix A.2.
 //
 // Mirror image of gru_fwd.cu: one CTA owns BT sequences for all T steps (t = T-1 .. 0), W_hh^T lives in
-// registers (thread (k,q) holds column k of W_hh for the row-slice q of each gate), the carried dh lives
-// in the registers of the lane that owns hidden unit k, the per-step dGH vector is exchanged through a
-// double-buffered shared-memory vector (one __syncthreads per step), saved r,z,n / q / h_{t-1} and dy
-// stream in through the bulk-async ring and dGI = [dar,daz,dan] / dq = dan*r stream out in place.
+// registers (lane q of the G-lane group of hidden unit k holds column k of W_hh for the row-slice q of each
+// gate), the carried dh lives in a register of the lane that owns (k, b) after the shuffle reduce-scatter,
+// the per-step dGH vector is exchanged through a double-buffered shared-memory vector (one __syncthreads
+// per step), saved r,z,n / q / h_{t-1} and dy stream in through the bulk-async ring and
+// dGI = [dar,daz,dan] / dq = dan*r stream out in place.
 // The weight-gradient contractions (K = B*T) and dX = dGI W_ih are separate GEMM kernels.
 #include "chunk_pipe.cuh"
 #include "kernels.h"
@@ -28,10 +29,19 @@ struct BwdParams {
   int bulk;
 };
 
+constexpr int DG_PAD = 16;  // dGH rows are HP+16 floats apart (bank spread between the sequences of a lane group)
+
+template <int HP, int G>
+constexpr int bwd_min_blocks() { return (HP * G <= 128) ? 3 : ((HP * G <= 256) ? 2 : 1); }
+
 template <int HP, int G, int BT, int TC, int NST>
-__global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel(BwdParams p) {
+__global__ void __launch_bounds__(HP* G, bwd_min_blocks<HP, G>()) gru_bwd_kernel(BwdParams p) {
   constexpr int KS = HP / G;
+  constexpr int NOWN = (BT >= G) ? BT / G : 1;
+  constexpr int HR = HP + DG_PAD;
   static_assert(KS % 4 == 0, "slice must be float4 granular");
+  static_assert(G == 2 || G == 4, "lane groups of 2 or 4");
+  static_assert(BT < G || BT % G == 0, "BT must be < G or a multiple of G");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int k = tid / G, ql = tid % G;
@@ -39,9 +49,9 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
-  float* dgs = reinterpret_cast<float*>(smem_raw);                     // [2][BT][3][HP]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dgs + 2 * BT * 3 * HP);
-  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * 3 * HP * 4 + NST * 8 + 127) / 128) * 128);
+  float* dgs = reinterpret_cast<float*>(smem_raw);                     // [2][BT][3][HR]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dgs + 2 * BT * 3 * HR);
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * 3 * HR * 4 + NST * 8 + 127) / 128) * 128);
 
   ChunkPipe<4, BT, TC, NST> pipe;
   pipe.g[0] = const_cast<float*>(p.rzn); pipe.gst[0] = p.dgi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | TG_STRM_STORE; pipe.shift[0] = 0;
@@ -64,10 +74,11 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel
         int jj = (i * G + ql) * 4 + c;
         wt[g][4 * i + c] = (k < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + k] : 0.f;
       }
-  for (int i = tid; i < 2 * BT * 3 * HP; i += HP * G) dgs[i] = 0.f;
-  float carry[BT];
+  for (int i = tid; i < 2 * BT * 3 * HR; i += HP * G) dgs[i] = 0.f;
+  // carry[o]: dL/dh_t[k] flowing in from step t+1 for the sequence this lane owns (b = o*G + ql, or b = ql)
+  float carry[NOWN];
 #pragma unroll
-  for (int b = 0; b < BT; ++b) carry[b] = 0.f;
+  for (int o = 0; o < NOWN; ++o) carry[o] = 0.f;
   pipe.start();
   __syncthreads();
 
@@ -79,13 +90,14 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel
     const int tcn = pipe.tcn_of(c);
     for (int tl = tcn - 1; tl >= 0; --tl) {
       const int t = t0 + tl;
-      float* dg = dgs + par * BT * 3 * HP;
-      float cz[BT];
-      // ---- pointwise gate derivatives for hidden unit k (lane b % G of the group handles sequence b) ----
+      float* dg = dgs + par * BT * 3 * HR;
+      float cz[NOWN];
+      // ---- pointwise gate derivatives for hidden unit k of the owned sequences ----
 #pragma unroll
-      for (int b = 0; b < BT; ++b) {
-        cz[b] = 0.f;
-        if (ql == (b % G) && k < H && b < nb) {
+      for (int o = 0; o < NOWN; ++o) {
+        const int b = (BT < G) ? ql : o * G + ql;
+        cz[o] = 0.f;
+        if (k < H && b < nb) {
           float* gp = pipe.row(s, 0, b, tl);
           float* qp = pipe.row(s, 1, b, tl);
           const float r = gp[k], z = gp[H + k], n = gp[2 * H + k], qv = qp[k];
@@ -93,18 +105,18 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel
           float dyv;
           if (p.dy_last) dyv = (t == T - 1) ? p.dy[(size_t)(b0 + b) * H + k] : 0.f;
           else dyv = pipe.row(s, 2, b, tl)[k];
-          const float dh = dyv + carry[b];
+          const float dh = dyv + carry[o];
           const float dn = dh * (1.f - z);
           const float dz = dh * (hp - n);
           const float dan = dn * (1.f - n * n);
           const float daz = dz * z * (1.f - z);
           const float dar = dan * qv * r * (1.f - r);
           const float dqv = dan * r;
-          cz[b] = dh * z;
+          cz[o] = dh * z;
           gp[k] = dar; gp[H + k] = daz; gp[2 * H + k] = dan; qp[k] = dqv;
-          dg[(b * 3 + 0) * HP + k] = dar;
-          dg[(b * 3 + 1) * HP + k] = daz;
-          dg[(b * 3 + 2) * HP + k] = dqv;
+          dg[(b * 3 + 0) * HR + k] = dar;
+          dg[(b * 3 + 1) * HR + k] = daz;
+          dg[(b * 3 + 2) * HR + k] = dqv;
         }
       }
       if (tl == 0 && pipe.bulk) fence_async_smem();
@@ -119,14 +131,43 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel
         for (int i = 0; i < KS / 4; ++i)
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
-            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 3 + g) * HP)[i * G + ql];
+            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 3 + g) * HR)[i * G + ql];
             acc[b] = fmaf(wt[g][4 * i + 0], dv.x, acc[b]);
             acc[b] = fmaf(wt[g][4 * i + 1], dv.y, acc[b]);
             acc[b] = fmaf(wt[g][4 * i + 2], dv.z, acc[b]);
             acc[b] = fmaf(wt[g][4 * i + 3], dv.w, acc[b]);
           }
+      // reduce-scatter over the lane group: the owner of (k, b) receives the complete sum
+      if constexpr (BT < G) {
+        float mine = 0.f;
 #pragma unroll
-      for (int b = 0; b < BT; ++b) carry[b] = cz[b] + group_sum<G>(acc[b]);
+        for (int b = 0; b < BT; ++b) {
+          const float v = group_sum<G>(acc[b]);
+          mine = (ql == b) ? v : mine;
+        }
+        carry[0] = cz[0] + mine;
+      } else if constexpr (G == 2) {
+#pragma unroll
+        for (int o = 0; o < NOWN; ++o) {
+          const float send = ql ? acc[2 * o] : acc[2 * o + 1];
+          const float keep = ql ? acc[2 * o + 1] : acc[2 * o];
+          carry[o] = cz[o] + keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+      } else {
+        const int hi = ql & 2, lo = ql & 1;
+#pragma unroll
+        for (int o = 0; o < NOWN; ++o) {
+          const float s0 = hi ? acc[4 * o + 0] : acc[4 * o + 2];
+          const float k0 = hi ? acc[4 * o + 2] : acc[4 * o + 0];
+          const float s1 = hi ? acc[4 * o + 1] : acc[4 * o + 3];
+          const float k1 = hi ? acc[4 * o + 3] : acc[4 * o + 1];
+          const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+          const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+          const float send = lo ? a0 : a1;
+          const float keep = lo ? a1 : a0;
+          carry[o] = cz[o] + keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+      }
       par ^= 1;
     }
     // the closing barrier of the chunk: all in-place writes of this stage happened before the last
@@ -139,7 +180,8 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_bwd_kernel
 template <int HP, int G, int BT, int TC, int NST>
 int launch_bwd(cudaStream_t st, const BwdParams& p) {
   const int widths[4] = {3 * p.H, p.H, p.H, p.H};
-  size_t smem = ((2 * BT * 3 * HP * 4 + NST * 8 + 127) / 128) * 128 +
+  constexpr int HR = HP + DG_PAD;
+  size_t smem = ((2 * BT * 3 * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<4, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_bwd_kernel<HP, G, BT, TC, NST>;
   static thread_local size_t configured = 0;
@@ -176,7 +218,7 @@ int tg_gru_bwd_impl(cudaStream_t st, const float* dy, const float* rzn, const fl
   p.bulk = (H % 4 == 0) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(y) && tg_aligned16(dgi) &&
            tg_aligned16(dq) && (p.dy_last || tg_aligned16(dy)) && !(flags & TG_GRU_NO_BULK);
   const int bto = (flags >> 8) & 0xff;
-  if (H <= 32) return dispatch_bt<32, 4>(st, p, tg_pick_bt(B, 32, bto));
-  if (H <= 64) return dispatch_bt<64, 4>(st, p, tg_pick_bt(B, 64, bto));
+  if (H <= 32) return dispatch_bt<32, 2>(st, p, tg_pick_bt(B, 32, bto));
+  if (H <= 64) return dispatch_bt<64, 2>(st, p, tg_pick_bt(B, 64, bto));
   return dispatch_bt<128, 4>(st, p, tg_pick_bt(B, 128, bto));
 }

@@ -3,11 +3,17 @@
 // Replaces the per-timestep loop inside torch.nn.GRU reached from timeGAN/timegan_model.py:32-34
 // (GRUStack.forward) -- math of SURVEY.md Appendix A.1, gate order r,z,n, h0 = 0.
 //
-// One CTA owns BT whole sequences for all T steps.  W_hh lives in registers (thread (j,q) holds the
-// three gate rows of hidden unit j for the k-slice q), h_{t-1} lives in a double-buffered shared-memory
-// vector, the pre-computed input projection gi (B,T,3H) streams in through a bulk-async (TMA) ring and
-// r,z,n / q / y stream out the same way (r,z,n overwrite gi in place, in smem and in HBM).
-// Exactly one __syncthreads per timestep.
+// One CTA owns BT whole sequences for all T steps.
+//   * W_hh lives in registers: the G lanes of a lane group share hidden unit j, lane q holds the k-slice
+//     {(i*G+q)*4 .. +3} of the three gate rows r_j, z_j, n_j  (3*HP/G registers).
+//   * h_{t-1} lives in a double-buffered shared-memory vector read as broadcast LDS.128; the copy a lane needs
+//     for the state update stays in a register.
+//   * the per-lane partial dot products are combined with a warp-shuffle REDUCE-SCATTER: after log2(G)
+//     exchange rounds lane q holds the complete gate pre-activations of the sequences b == q (mod G), so every
+//     lane evaluates sigmoid/tanh for a different (j, b) -- no idle lanes in the transcendental part.
+//   * gi = X W_ih^T + b_ih (B,T,3H) streams in through a bulk-async (TMA engine) ring of TC-step chunks; y and,
+//     when the backward pass will follow, r,z,n (over gi, in place) and q = h W_hn^T + b_hn stream out the
+//     same way.  Exactly one __syncthreads per timestep.
 #include "chunk_pipe.cuh"
 #include "kernels.h"
 
@@ -24,10 +30,19 @@ struct FwdParams {
   int bulk;
 };
 
+constexpr int HS_PAD = 16;  // h rows are HP+16 floats apart: the two sequences a lane pair writes hit different banks
+
+template <int HP, int G, int BT>
+constexpr int fwd_min_blocks() { return (HP * G <= 128) ? 3 : ((HP * G <= 256) ? 2 : 1); }
+
 template <int HP, int G, int BT, int TC, int NST>
-__global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel(FwdParams p) {
-  constexpr int KS = HP / G;  // k values per lane
+__global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_kernel(FwdParams p) {
+  constexpr int KS = HP / G;                     // k values per lane
+  constexpr int NOWN = (BT >= G) ? BT / G : 1;   // sequences a lane finishes per step
+  constexpr int HR = HP + HS_PAD;
   static_assert(KS % 4 == 0, "k-slice must be float4 granular");
+  static_assert(G == 2 || G == 4, "lane groups of 2 or 4");
+  static_assert(BT < G || BT % G == 0, "BT must be < G or a multiple of G");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int j = tid / G, ql = tid % G;
@@ -36,9 +51,9 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel
   const int nb = min(BT, p.B - b0);
 
   // ---- shared memory carve-up ----
-  float* hs = reinterpret_cast<float*>(smem_raw);                         // [2][BT][HP]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * BT * HP);          // [NST] (8-B aligned: 2*BT*HP*4 % 8 == 0)
-  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128);
+  float* hs = reinterpret_cast<float*>(smem_raw);                 // [2][BT][HR]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * BT * HR);  // [NST]
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128);
 
   ChunkPipe<3, BT, TC, NST> pipe;
   pipe.g[0] = pipe.gst[0] = p.gi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | (p.save ? TG_STRM_STORE : 0); pipe.shift[0] = 0;
@@ -63,7 +78,10 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel
         w[g][4 * i + c] = (j < H && k < H) ? p.whh[(size_t)(g * H + j) * H + k] : 0.f;
       }
   }
-  for (int i = tid; i < 2 * BT * HP; i += HP * G) hs[i] = 0.f;
+  for (int i = tid; i < 2 * BT * HR; i += HP * G) hs[i] = 0.f;
+  float hprev[NOWN];
+#pragma unroll
+  for (int o = 0; o < NOWN; ++o) hprev[o] = 0.f;
   pipe.start();
   __syncthreads();
 
@@ -73,8 +91,8 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel
     const int s = c % NST;
     const int tcn = pipe.tcn_of(c);
     for (int tl = 0; tl < tcn; ++tl) {
-      const float* hc = hs + cur * BT * HP;
-      float* hn = hs + (cur ^ 1) * BT * HP;
+      const float* hc = hs + cur * BT * HR;
+      float* hn = hs + (cur ^ 1) * BT * HR;
       float acc[BT][3];
 #pragma unroll
       for (int b = 0; b < BT; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
@@ -82,7 +100,7 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel
       for (int i = 0; i < KS / 4; ++i) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-          const float4 hv = reinterpret_cast<const float4*>(hc + b * HP)[i * G + ql];
+          const float4 hv = reinterpret_cast<const float4*>(hc + b * HR)[i * G + ql];
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             acc[b][g] = fmaf(w[g][4 * i + 0], hv.x, acc[b][g]);
@@ -92,19 +110,61 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel
           }
         }
       }
+      // ---- combine the G partial sums: own[o][g] = complete sum for sequence b = o*G + ql ----
+      float own[NOWN][3];
+      if constexpr (BT < G) {
+        // fewer sequences than lanes: butterfly, lane b finishes sequence b
 #pragma unroll
-      for (int b = 0; b < BT; ++b) {
+        for (int b = 0; b < BT; ++b)
 #pragma unroll
-        for (int g = 0; g < 3; ++g) acc[b][g] = group_sum<G>(acc[b][g]);
-        if (ql == (b % G) && j < H && b < nb) {
+          for (int g = 0; g < 3; ++g) acc[b][g] = group_sum<G>(acc[b][g]);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          own[0][g] = acc[0][g];
+#pragma unroll
+          for (int b = 1; b < BT; ++b) own[0][g] = (ql == b) ? acc[b][g] : own[0][g];
+        }
+      } else if constexpr (G == 2) {
+#pragma unroll
+        for (int o = 0; o < NOWN; ++o)
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            const float send = ql ? acc[2 * o][g] : acc[2 * o + 1][g];
+            const float keep = ql ? acc[2 * o + 1][g] : acc[2 * o][g];
+            own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+      } else {  // G == 4
+        const int hi = ql & 2, lo = ql & 1;
+#pragma unroll
+        for (int o = 0; o < NOWN; ++o)
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            // round 1 (xor 2): keep the pair {4o + (hi), 4o + (hi) + 1}
+            const float s0 = hi ? acc[4 * o + 0][g] : acc[4 * o + 2][g];
+            const float k0 = hi ? acc[4 * o + 2][g] : acc[4 * o + 0][g];
+            const float s1 = hi ? acc[4 * o + 1][g] : acc[4 * o + 3][g];
+            const float k1 = hi ? acc[4 * o + 3][g] : acc[4 * o + 1][g];
+            const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+            const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+            // round 2 (xor 1)
+            const float send = lo ? a0 : a1;
+            const float keep = lo ? a1 : a0;
+            own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+          }
+      }
+      // ---- gates + state update for the sequences this lane owns ----
+#pragma unroll
+      for (int o = 0; o < NOWN; ++o) {
+        const int b = (BT < G) ? ql : o * G + ql;
+        if (j < H && b < nb) {
           float* gp = pipe.row(s, 0, b, tl);
-          const float hp = hc[b * HP + j];
-          const float r = sigmoid_acc(gp[j] + acc[b][0] + bh[0]);
-          const float z = sigmoid_acc(gp[H + j] + acc[b][1] + bh[1]);
-          const float qv = acc[b][2] + bh[2];
-          const float n = tanh_acc(gp[2 * H + j] + r * qv);
-          const float h = n + z * (hp - n);
-          hn[b * HP + j] = h;
+          const float r = sigmoid_fast(gp[j] + own[o][0] + bh[0]);
+          const float z = sigmoid_fast(gp[H + j] + own[o][1] + bh[1]);
+          const float qv = own[o][2] + bh[2];
+          const float n = tanh_fast(fmaf(r, qv, gp[2 * H + j]));
+          const float h = fmaf(z, hprev[o] - n, n);
+          hprev[o] = h;
+          hn[b * HR + j] = h;
           pipe.row(s, 2, b, tl)[j] = h;
           if (p.save) {
             gp[j] = r; gp[H + j] = z; gp[2 * H + j] = n;
@@ -123,8 +183,9 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_fwd_kernel
 
 template <int HP, int G, int BT, int TC, int NST>
 int launch_fwd(cudaStream_t st, const FwdParams& p) {
+  constexpr int HR = HP + HS_PAD;
   const int widths[3] = {3 * p.H, p.H, p.H};
-  size_t smem = ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128 +
+  size_t smem = ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<3, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_fwd_kernel<HP, G, BT, TC, NST>;
   static thread_local size_t configured = 0;
@@ -152,12 +213,15 @@ int dispatch_bt(cudaStream_t st, const FwdParams& p, int bt) {
 
 }  // namespace
 
+// Sequences per CTA.  A CTA's cost per step grows far slower than BT (the weight registers are reused for every
+// sequence), so prefer BT = 2 as soon as that still gives every SM a CTA, and BT = 4 once even that oversubscribes
+// the resident-CTA capacity.
 int tg_pick_bt(int B, int HP, int bt_override) {
   if (bt_override == 1 || bt_override == 2 || bt_override == 4) return bt_override;
-  const int occ = (HP <= 64) ? 2 : 1;
-  const int cap = tg_num_sms() * occ;
-  if (B <= cap) return 1;
-  if (B <= 2 * cap) return 2;
+  const int sms = tg_num_sms();
+  const int occ = (HP <= 64) ? 3 : 1;
+  if (B < sms) return 1;                 // fewer sequences than SMs: one per CTA, spread as wide as possible
+  if (B <= 2 * sms * occ) return 2;
   return 4;
 }
 
@@ -172,7 +236,7 @@ int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* b
   p.bulk = (H % 4 == 0) && tg_aligned16(gi) && tg_aligned16(y) && (!save || tg_aligned16(q)) &&
            !(flags & TG_GRU_NO_BULK);
   const int bto = (flags >> 8) & 0xff;
-  if (H <= 32) return dispatch_bt<32, 4>(st, p, tg_pick_bt(B, 32, bto));
-  if (H <= 64) return dispatch_bt<64, 4>(st, p, tg_pick_bt(B, 64, bto));
+  if (H <= 32) return dispatch_bt<32, 2>(st, p, tg_pick_bt(B, 32, bto));
+  if (H <= 64) return dispatch_bt<64, 2>(st, p, tg_pick_bt(B, 64, bto));
   return dispatch_bt<128, 4>(st, p, tg_pick_bt(B, 128, bto));
 }
