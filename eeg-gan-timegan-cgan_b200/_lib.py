@@ -14,7 +14,7 @@ LIB_PATH = _PKG / "libtimegan_b200.so"
 
 # flags (keep in sync with include/timegan_b200.h)
 GRU_SAVE, GRU_NO_BULK, GRU_DY_LAST = 1, 2, 4
-PROJ_FP32, PROJ_BF16 = 0, 1
+PROJ_FP32, PROJ_BF16, PROJ_TF32X3 = 0, 1, 2
 
 if not LIB_PATH.exists():
     raise ImportError(

@@ -124,9 +124,10 @@ int tg_prof_read(int kind, double* ms, long long* calls, double* bytes, double* 
 int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
             int M, int N, int K, int accumulate, int mode) {
   ProfScope _ps(stream, K_PROJ, 4.0 * ((double)M * K + (double)N * K + (double)M * N), 2.0 * M * N * K);
-  if (mode == TG_PROJ_BF16) {
-    int rc = tg_proj_tc_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
-    if (rc != TG_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core tile cannot take run exact fp32
+  if (mode == TG_PROJ_BF16 || mode == TG_PROJ_TF32X3) {
+    int rc = tg_proj_tc_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate,
+                             mode == TG_PROJ_TF32X3 ? 3 : 1);
+    if (rc != TG_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core tile cannot take run on the FFMA path
   }
   return tg_gemm_nt_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
 }

@@ -33,7 +33,7 @@ size_t tg_wgrad_ws_bytes(int M, int N, int K);
 
 // tensor-core projection (tcgen05 + TMA); returns TG_ERR_UNSUPPORTED for shapes it cannot take
 int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
-                    int ldc, int M, int N, int K, int accumulate);
+                    int ldc, int M, int N, int K, int accumulate, int passes);
 
 // column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)
 size_t tg_colsum_ws_bytes(int N);

@@ -22,15 +22,25 @@ _PROJ_MODE = _lib.PROJ_FP32
 _BT_OVERRIDE = 0  # sequences per CTA override for the recurrent kernels (0 = heuristic)
 
 
+_MODES = {"ffma": _lib.PROJ_FP32, "fp32": _lib.PROJ_FP32, "bf16": _lib.PROJ_BF16, "tf32": _lib.PROJ_BF16,
+          "tf32x3": _lib.PROJ_TF32X3}
+_MODE_NAME = "fp32"
+
+
 def set_proj_mode(mode: str):
-    global _PROJ_MODE
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("proj mode must be 'fp32' or 'bf16'")
-    _PROJ_MODE = _lib.PROJ_FP32 if mode == "fp32" else _lib.PROJ_BF16
+    """Precision of the time-batched contractions (input projections, dX, heads):
+    "ffma"   exact fp32 on CUDA cores;
+    "tf32x3" tcgen05 tensor cores, 3xTF32 split (fp32-parity mode, 1e-4);
+    "fp32"   alias of the fp32-parity mode in use (see _MODES);
+    "bf16" / "tf32"  tcgen05 tensor cores, one TF32 pass (reduced-precision projection mode, 2e-2)."""
+    global _PROJ_MODE, _MODE_NAME
+    if mode not in _MODES:
+        raise ValueError(f"proj mode must be one of {sorted(_MODES)}")
+    _PROJ_MODE, _MODE_NAME = _MODES[mode], mode
 
 
 def get_proj_mode() -> str:
-    return "fp32" if _PROJ_MODE == _lib.PROJ_FP32 else "bf16"
+    return _MODE_NAME
 
 
 def set_bt_override(bt: int):
@@ -83,6 +93,12 @@ def dgrad(dg2d: torch.Tensor, w: torch.Tensor, out2d: Optional[torch.Tensor] = N
     N = w.shape[1]
     if out2d is None:
         out2d = torch.empty(M, N, dtype=torch.float32, device=dg2d.device)
+    if _PROJ_MODE != _lib.PROJ_FP32:
+        # tensor-core path: the same TN kernel as the projection, with the (small) weight transposed to K-major
+        wt = w.t().contiguous()
+        check(lib.tg_proj(stream_ptr(), ptr(dg2d), dg2d.stride(0), ptr(wt), wt.stride(0), None, ptr(out2d),
+                          out2d.stride(0), M, N, K, int(accumulate), _PROJ_MODE), "tg_proj(dgrad)")
+        return out2d
     check(lib.tg_dgrad(stream_ptr(), ptr(dg2d), dg2d.stride(0), ptr(w), w.stride(0), ptr(out2d), out2d.stride(0),
                        M, N, K, int(accumulate)), "tg_dgrad")
     return out2d
@@ -208,7 +224,8 @@ def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Seque
         w_ih, w_hh, _, _ = _layer_weights(weights, l)
         H = w_hh.shape[1]
         gid = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
-        proj(tin.view(B * T, -1), w_ih, None, gid.view(B * T, 3 * H), mode=_lib.PROJ_FP32)
+        proj(tin.view(B * T, -1), w_ih, None, gid.view(B * T, 3 * H),
+             mode=_lib.PROJ_FP32 if _PROJ_MODE == _lib.PROJ_BF16 else _PROJ_MODE)
         ydot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         qdot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         check(lib.tg_gru_jvp_fwd(stream_ptr(), ptr(gid), ptr(sv.rzn), ptr(sv.q), ptr(sv.y), ptr(w_hh), ptr(ydot),

@@ -37,8 +37,10 @@ extern "C" {
 #define TG_GRU_DY_LAST 4 /* backward: the output gradient is (B,H) and applies to t = T-1 only */
 
 /* projection precision */
-#define TG_PROJ_FP32 0 /* CUDA-core FFMA, exact fp32 (parity mode, 1e-4) */
-#define TG_PROJ_BF16 1 /* tcgen05 tensor cores, bf16 operands / fp32 accumulate (2e-2 mode) */
+#define TG_PROJ_FP32 0   /* CUDA-core FFMA, exact fp32 */
+#define TG_PROJ_BF16 1   /* tcgen05 tensor cores, one TF32 pass over the fp32 operands (reduced-precision projection
+                            mode, bound 2e-2; TF32 keeps 10 mantissa bits vs bf16's 7 and needs no conversion pass) */
+#define TG_PROJ_TF32X3 2 /* tcgen05 tensor cores, 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-parity mode, 1e-4 */
 
 int tg_version(void);
 const char* tg_last_error(void);

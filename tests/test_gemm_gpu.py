@@ -45,12 +45,42 @@ def test_wgrad_shifted_rows():
     assert relerr(dW, ref) < 1e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(24576, 72, 24), (4096, 192, 64), (1000, 384, 128), (777, 72, 14)])
-def test_proj_bf16_mode(M, N, K):
+TC_SHAPES = [(24576, 72, 24), (4096, 192, 64), (1000, 384, 128), (777, 72, 14), (128, 16, 4), (5000, 168, 28),
+             (3000, 64, 192), (1300, 24, 72), (196608, 192, 64)]
+
+
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+@pytest.mark.parametrize("mode,tol", [("tf32", 2e-2), ("tf32x3", 2e-6)])
+def test_proj_tensor_core_modes(M, N, K, mode, tol):
+    """tcgen05 projection: one TF32 pass (the 2e-2 'bf16-class' mode; measured ~5e-4) and 3xTF32 (fp32 parity).
+    Shapes the tile cannot take (K % 4 != 0) fall back to the FFMA kernel inside tg_proj and still pass."""
     from timegan_b200 import ops, _lib
     g = torch.Generator().manual_seed(M + 1)
-    A = torch.rand(M, K, generator=g)
+    A = torch.rand(M, K, generator=g) * 2 - 0.7
     W = torch.randn(N, K, generator=g) / K ** 0.5
     b = torch.randn(N, generator=g)
-    C = ops.proj(A.to(DEV), W.to(DEV), b.to(DEV), mode=_lib.PROJ_BF16)
-    assert relerr(C, A.double() @ W.double().T + b.double()) < 2e-2
+    ref = A.double() @ W.double().T + b.double()
+    C = ops.proj(A.to(DEV), W.to(DEV), b.to(DEV), mode=ops._MODES[mode])
+    err = relerr(C, ref)
+    assert err < tol, err
+    assert err < 2e-3          # even the single pass is far inside its 2e-2 budget
+    # accumulate and no-bias variants
+    C2 = ops.proj(A.to(DEV), W.to(DEV), None, out2d=C.clone(), mode=ops._MODES[mode], accumulate=True)
+    assert relerr(C2, 2 * ref - b.double()) < max(tol, 2e-6) * 2
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 64, 192), (2000, 24, 72), (1500, 28, 168)])
+def test_dgrad_through_tensor_cores(M, N, K):
+    from timegan_b200 import ops
+    g = torch.Generator().manual_seed(K)
+    dG = torch.randn(M, K, generator=g)
+    W = torch.randn(K, N, generator=g) / K ** 0.5
+    ref = dG.double() @ W.double()
+    old = ops.get_proj_mode()
+    try:
+        ops.set_proj_mode("tf32x3")
+        assert relerr(ops.dgrad(dG.to(DEV), W.to(DEV)), ref) < 2e-6
+        ops.set_proj_mode("tf32")
+        assert relerr(ops.dgrad(dG.to(DEV), W.to(DEV)), ref) < 2e-3
+    finally:
+        ops.set_proj_mode(old)
