@@ -81,6 +81,19 @@ int tg_num_sms() {
   return sms;
 }
 
+int tg_max_optin_smem() {
+  static std::atomic<int> v{0};
+  int x = v.load();
+  if (x == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&x, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || x <= 0)
+      return 227 * 1024;
+    v.store(x);
+  }
+  return x;
+}
+
 size_t tg_sumsq_ws_bytes(int n, const long long* sizes);
 
 extern "C" {
@@ -138,11 +151,19 @@ int tg_dgrad(void* stream, const float* dG, int ldg, const float* W, int ldw, fl
   return tg_gemm_nn_impl((cudaStream_t)stream, dG, ldg, W, ldw, dX, ldx, M, N, K, accumulate);
 }
 
-size_t tg_wgrad_workspace_bytes(int M, int N, int K) { return tg_wgrad_ws_bytes(M, N, K); }
+size_t tg_wgrad_workspace_bytes(int M, int N, int K) {
+  const size_t a = tg_wgrad_ws_bytes(M, N, K), b = tg_wgrad_tc_ws_bytes(M, N, K);
+  return a > b ? a : b;
+}
 
 int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
-             int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes) {
+             int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes, int mode) {
   ProfScope _ps(stream, K_WGRAD, 4.0 * ((double)M * N + (double)M * K + (double)N * K), 2.0 * M * N * K);
+  if (mode == TG_PROJ_BF16 || mode == TG_PROJ_TF32X3) {
+    int rc = tg_wgrad_tc_impl((cudaStream_t)stream, dG, ldg, A, lda, dW, lddw, db, M, N, K, a_shift_T, accumulate,
+                              (float*)ws, ws_bytes, mode == TG_PROJ_TF32X3 ? 3 : 1);
+    if (rc != TG_ERR_UNSUPPORTED) return rc;
+  }
   return tg_wgrad_impl((cudaStream_t)stream, dG, ldg, A, lda, dW, lddw, db, M, N, K, a_shift_T, accumulate, (float*)ws,
                        ws_bytes);
 }

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 // ---- status codes (mirrors include/timegan_b200.h) -------------------------------------------
 #define TG_OK 0
@@ -22,6 +23,28 @@ int tg_check_launch(const char* what);   // returns 0 or positive cudaError_t, s
       tg_set_error(__VA_ARGS__);               \
       return (code);                           \
     }                                          \
+  } while (0)
+
+// Opt a kernel in to the device's maximum dynamic shared memory, once per (kernel, device).  The attribute is a
+// process-wide property of the function: setting it to "what this launch needs" from two host threads (forward on
+// the main thread, backward on autograd's) lets the smaller request silently lower the limit for the other.
+int tg_max_optin_smem();
+#define TG_OPT_IN_SMEM(kern, what)                                                                          \
+  do {                                                                                                      \
+    static std::atomic<unsigned> _tg_done{0};                                                               \
+    int _dev = 0;                                                                                           \
+    cudaGetDevice(&_dev);                                                                                   \
+    const unsigned _bit = 1u << (_dev & 31);                                                                \
+    if (!(_tg_done.load(std::memory_order_acquire) & _bit)) {                                               \
+      cudaError_t _e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                            tg_max_optin_smem());                                           \
+      if (_e != cudaSuccess) {                                                                              \
+        tg_set_error("%s: cannot opt in to %d B of shared memory: %s", what, tg_max_optin_smem(),           \
+                     cudaGetErrorString(_e));                                                               \
+        return (int)_e;                                                                                     \
+      }                                                                                                     \
+      _tg_done.fetch_or(_bit, std::memory_order_release);                                                   \
+    }                                                                                                       \
   } while (0)
 
 static inline bool tg_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -188,12 +188,8 @@ int launch_fwd(cudaStream_t st, const FwdParams& p) {
   size_t smem = ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<3, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_fwd_kernel<HP, G, BT, TC, NST>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { tg_set_error("gru_fwd: smem attr %zu B: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  TG_OPT_IN_SMEM(kern, "gru_fwd");
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_fwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   dim3 grid((p.B + BT - 1) / BT), block(HP * G);
   kern<<<grid, block, smem, st>>>(p);
   return tg_check_launch("gru_fwd");

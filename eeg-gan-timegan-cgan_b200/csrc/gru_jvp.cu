@@ -303,12 +303,8 @@ int launch_jf(cudaStream_t st, const JfParams& p) {
   size_t smem = ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<6, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_jvp_fwd_kernel<HP, G, BT, TC, NST>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { tg_set_error("gru_jvp_fwd: smem attr %zu B: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  TG_OPT_IN_SMEM(kern, "gru_jvp_fwd");
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_jvp_fwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   kern<<<dim3((p.B + BT - 1) / BT), dim3(HP * G), smem, st>>>(p);
   return tg_check_launch("gru_jvp_fwd");
 }
@@ -319,12 +315,8 @@ int launch_jb(cudaStream_t st, const JbParams& p) {
   size_t smem = ((2 * BT * 6 * HP * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<8, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_jvp_bwd_kernel<HP, G, BT, TC, NST>;
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { tg_set_error("gru_jvp_bwd: smem attr %zu B: %s", smem, cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  TG_OPT_IN_SMEM(kern, "gru_jvp_bwd");
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_jvp_bwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   kern<<<dim3((p.B + BT - 1) / BT), dim3(HP * G), smem, st>>>(p);
   return tg_check_launch("gru_jvp_bwd");
 }

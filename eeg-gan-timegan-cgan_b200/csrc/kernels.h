@@ -35,6 +35,13 @@ size_t tg_wgrad_ws_bytes(int M, int N, int K);
 int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
                     int ldc, int M, int N, int K, int accumulate, int passes);
 
+// tensor-core weight gradient (tcgen05, MN-major operands); TG_ERR_UNSUPPORTED for shapes it cannot take
+size_t tg_wgrad_tc_ws_bytes(int M, int N, int K);
+int tg_wgrad_tc_impl(cudaStream_t st, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw,
+                     float* db, int M, int N, int K, int a_shift_T, int accumulate, float* ws, size_t ws_bytes,
+                     int passes);
+int tg_max_optin_smem();
+
 // column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)
 size_t tg_colsum_ws_bytes(int N);
 int tg_colsum_impl(cudaStream_t st, const float* X, int ld, int M, int N, float* out, int accumulate, float* ws,

@@ -255,12 +255,8 @@ int tg_acf_fwd_impl(cudaStream_t st, const float* xz, int B, int T, int C, int L
   TG_REQUIRE(B > 0 && T > 1 && C > 0 && L >= 1 && L < T, TG_ERR_SHAPE, "acf_fwd: bad shape B=%d T=%d C=%d L=%d", B, T, C, L);
   size_t smem = (size_t)T * C * 4;
   TG_REQUIRE(smem <= 200 * 1024, TG_ERR_UNSUPPORTED, "acf_fwd: T*C=%d too large for one CTA", T * C);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(acf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { tg_set_error("acf_fwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  TG_OPT_IN_SMEM(acf_fwd_kernel, "acf_fwd");
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("acf_fwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   acf_fwd_kernel<<<B, 256, smem, st>>>(xz, T, C, L, part);
   return tg_check_launch("acf_fwd");
 }
@@ -271,12 +267,8 @@ int tg_acf_bwd_impl(cudaStream_t st, const float* xz, const float* S, int B, int
   TG_REQUIRE(B > 0 && T > 1 && C > 0 && L >= 1 && L < T, TG_ERR_SHAPE, "acf_bwd: bad shape");
   size_t smem = ((size_t)T * C + (size_t)L * C + 2 * C) * 4;
   TG_REQUIRE(smem <= 200 * 1024, TG_ERR_UNSUPPORTED, "acf_bwd: T*C=%d too large for one CTA", T * C);
-  static thread_local size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(acf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { tg_set_error("acf_bwd: smem attr: %s", cudaGetErrorString(e)); return (int)e; }
-    configured = smem;
-  }
+  TG_OPT_IN_SMEM(acf_bwd_kernel, "acf_bwd");
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("acf_bwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   acf_bwd_kernel<<<B, 256, smem, st>>>(xz, S, T, C, L, gz, stat);
   return tg_check_launch("acf_bwd");
 }

@@ -270,22 +270,11 @@ int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, in
   if (gx > num_tiles) gx = num_tiles;
   if (gx < 1) gx = 1;
   dim3 grid(gx, n_tiles);
-  cudaError_t e;
   if (passes == 3) {
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-      e = cudaFuncSetAttribute(tc_gemm_tn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { tg_set_error("proj_tc: smem attr %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-      configured = smem;
-    }
+    TG_OPT_IN_SMEM(tc_gemm_tn_kernel<3>, "proj_tc");
     tc_gemm_tn_kernel<3><<<grid, NUM_THREADS_3P, smem, st>>>(tmA, tmW, p);
   } else {
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-      e = cudaFuncSetAttribute(tc_gemm_tn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) { tg_set_error("proj_tc: smem attr %zu: %s", smem, cudaGetErrorString(e)); return (int)e; }
-      configured = smem;
-    }
+    TG_OPT_IN_SMEM(tc_gemm_tn_kernel<1>, "proj_tc");
     tc_gemm_tn_kernel<1><<<grid, NUM_THREADS_1P, smem, st>>>(tmA, tmW, p);
   }
   return tg_check_launch("proj_tc");

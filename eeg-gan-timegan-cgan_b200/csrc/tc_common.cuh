@@ -25,9 +25,10 @@ static inline tg_encode_tiled_fn tg_get_encode_tiled() {
 }
 
 // fp32 row-major matrix [rows][cols] with leading dimension ld (floats) -> 2-D map, box = box_cols x box_rows,
-// 128-byte swizzle (box_cols * 4 must be 128), out-of-bounds elements read as zero.
+// 128-byte swizzle (box_cols * 4 must be 128), out-of-bounds elements read as zero.  atom32 selects the
+// 128B-span / 32B-atom swizzle, the only layout tcgen05 accepts for MN-major 32-bit (TF32) operands.
 static inline int tg_make_map_2d(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld,
-                                 int box_cols, int box_rows) {
+                                 int box_cols, int box_rows, bool atom32 = false) {
   tg_encode_tiled_fn enc = tg_get_encode_tiled();
   if (!enc) { tg_set_error("cuTensorMapEncodeTiled unavailable"); return TG_ERR_UNSUPPORTED; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -35,7 +36,9 @@ static inline int tg_make_map_2d(CUtensorMap* map, const float* base, long long 
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { tg_set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r); return TG_ERR_ARG; }
   return TG_OK;
@@ -96,6 +99,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t base, uint32_t cols) {
 //   K-major  operand: rows 128 B apart, 8-row groups SBO = 1024 B apart (LBO unused, set to 1).
 //   MN-major operand: 128-B rows hold 32 consecutive MN elements, 8 K-rows per 1024-B group (SBO),
 //                     successive 32-element MN chunks LBO bytes apart.
+//   MN-major TF32 operand (layout type SWIZZLE_128B_BASE32B): 128-B rows hold 32 consecutive MN elements,
+//                     4 K-rows per 512-byte swizzle atom (SBO = 512 for densely stacked rows), MN chunks LBO apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;  // descriptor version (Blackwell)
+  d |= 1ull << 61;  // SWIZZLE_128B_BASE32B
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);

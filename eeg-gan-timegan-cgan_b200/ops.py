@@ -18,11 +18,11 @@ from . import _lib
 from ._lib import lib, check, ptr, stream_ptr, require_cuda
 
 # process-wide projection mode for the GRU input projections ("fp32" exact, "bf16" tensor-core mode)
-_PROJ_MODE = _lib.PROJ_FP32
+_PROJ_MODE = _lib.PROJ_TF32X3
 _BT_OVERRIDE = 0  # sequences per CTA override for the recurrent kernels (0 = heuristic)
 
 
-_MODES = {"ffma": _lib.PROJ_FP32, "fp32": _lib.PROJ_FP32, "bf16": _lib.PROJ_BF16, "tf32": _lib.PROJ_BF16,
+_MODES = {"ffma": _lib.PROJ_FP32, "fp32": _lib.PROJ_TF32X3, "bf16": _lib.PROJ_BF16, "tf32": _lib.PROJ_BF16,
           "tf32x3": _lib.PROJ_TF32X3}
 _MODE_NAME = "fp32"
 
@@ -105,14 +105,15 @@ def dgrad(dg2d: torch.Tensor, w: torch.Tensor, out2d: Optional[torch.Tensor] = N
 
 
 def wgrad(dg2d: torch.Tensor, a2d: torch.Tensor, dw: torch.Tensor, db: Optional[torch.Tensor], n_cols: int,
-          shift_T: int = 0, accumulate: bool = False):
+          shift_T: int = 0, accumulate: bool = False, mode: Optional[int] = None):
     """dw[N,K] (+)= dg[:, :N]^T @ a ; db[N] (+)= colsum(dg[:, :N]).  shift_T>0: a row m := a[m-1], 0 at m%T==0."""
     M = dg2d.shape[0]
     K = a2d.shape[1]
     nbytes = lib.tg_wgrad_workspace_bytes(M, n_cols, K)
     ws = _ws(nbytes, dg2d.device)
     check(lib.tg_wgrad(stream_ptr(), ptr(dg2d), dg2d.stride(0), ptr(a2d), a2d.stride(0), ptr(dw), dw.stride(0),
-                       ptr(db), M, n_cols, K, shift_T, int(accumulate), ptr(ws), nbytes), "tg_wgrad")
+                       ptr(db), M, n_cols, K, shift_T, int(accumulate), ptr(ws), nbytes,
+                       _PROJ_MODE if mode is None else mode), "tg_wgrad")
 
 
 def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 1
+#define TG_ABI_VERSION 2
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -75,7 +75,7 @@ int tg_dgrad(void* stream, const float* dG, int ldg, const float* W, int ldw, fl
  * the layer output y).  Deterministic split-M reduction through `ws` (>= tg_wgrad_workspace_bytes). */
 size_t tg_wgrad_workspace_bytes(int M, int N, int K);
 int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
-             int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes);
+             int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes, int mode /* TG_PROJ_* */);
 
 /* ---- persistent fused GRU layer forward (timegan_model.py:32-34 -> nn.GRU per-timestep loop) --------------
  * gi (B,T,3H) holds X W_ih^T + b_ih on entry; with TG_GRU_SAVE it holds r,z,n on exit and q (B,T,H) receives

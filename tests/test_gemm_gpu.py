@@ -84,3 +84,33 @@ def test_dgrad_through_tensor_cores(M, N, K):
         assert relerr(ops.dgrad(dG.to(DEV), W.to(DEV)), ref) < 2e-3
     finally:
         ops.set_proj_mode(old)
+
+
+@pytest.mark.parametrize("M,N,K,T", [(24576, 72, 24, 768), (6000, 192, 64, 200), (4096, 128, 64, 0), (3000, 168, 56, 100),
+                                     (196608, 192, 64, 768), (5000, 64, 64, 50), (2048, 384, 128, 64), (1000, 24, 24, 0)])
+@pytest.mark.parametrize("mode,tol", [("tf32", 3e-3), ("tf32x3", 2e-5)])
+def test_wgrad_tensor_core_modes(M, N, K, T, mode, tol):
+    """tcgen05 weight gradients (MN-major operands) incl. the h_{t-1} row shift and the fused bias gradient,
+    from a strided column slice of a wider dG (as the BPTT kernels' outputs are consumed)."""
+    from timegan_b200 import ops
+    g = torch.Generator().manual_seed(N + K)
+    ldg = N + 64
+    dG_full = torch.randn(M, ldg, generator=g)
+    A = torch.rand(M, K, generator=g) - 0.3
+    dG = dG_full[:, :N]
+    if T > 0:
+        B = M // T
+        Ash = torch.cat([torch.zeros(B, 1, K), A.view(B, T, K)[:, :-1]], 1).reshape(M, K)
+    else:
+        Ash = A
+    ref_w = dG.double().T @ Ash.double()
+    ref_b = dG.double().sum(0)
+    dGd = dG_full.to(DEV)[:, :N]
+    dW = torch.full((N, K), 7.0, device=DEV)
+    db = torch.full((N,), 7.0, device=DEV)
+    ops.wgrad(dGd, A.to(DEV), dW, db, N, shift_T=T, mode=ops._MODES[mode])
+    assert relerr(dW, ref_w) < tol, relerr(dW, ref_w)
+    assert relerr(db, ref_b) < 1e-5
+    ops.wgrad(dGd, A.to(DEV), dW, None, N, shift_T=T, accumulate=True, mode=ops._MODES[mode])
+    assert relerr(dW, 2 * ref_w) < tol
+    assert relerr(db, ref_b) < 1e-5      # untouched when db is not requested
