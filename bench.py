@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--proj", type=str, default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="disable side-stream concurrency inside the step")
     ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
     return ap.parse_args()
 
@@ -198,8 +199,11 @@ def run_ours(a):
     import timegan_b200 as tg
     from timegan_b200 import _lib, ops, dist as tdist, train_timegan as tt
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
         tdist.init(backend="nccl", device=dev)
     ops.set_proj_mode(a.proj)
+    tt.set_concurrency(not a.serial)
 
     torch.manual_seed(42)
     model = tg.TimeGAN(X_DIM, a.hidden, a.hidden, a.layers, 0.0).to(dev)
@@ -270,6 +274,8 @@ def run_ours(a):
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     assert all(v == v for v in scal.tolist()), f"non-finite losses in bench: {scal.tolist()}"
 
+    if world > 1:
+        td.destroy_process_group()
     if rank != 0:
         return
     peaks = {}

@@ -178,6 +178,47 @@ def _reduce_and_step(opt, params, clip):
     clip_and_step(opt, params, clip)
 
 
+_SIDE_STREAMS: Dict[str, list] = {}
+_CONCURRENT = True   # run the independent GRU stacks of a step on side streams (set False to serialise everything)
+
+
+def set_concurrency(on: bool):
+    global _CONCURRENT
+    _CONCURRENT = bool(on)
+
+
+class _Fork:
+    """`with _Fork(device, k):` runs the block on side stream k after it has caught up with the current stream.
+    The recurrent kernels are latency-bound (768 dependent steps per layer pass) and leave most of each SM idle,
+    so independent stacks of a step (E || G->S, D || R, and their BPTTs, which autograd replays on the stream of
+    the forward) overlap almost for free.  join() makes the current stream wait for every forked stream."""
+
+    def __init__(self, device, k: int):
+        self.main = torch.cuda.current_stream(device)
+        if _CONCURRENT:
+            pool = _SIDE_STREAMS.setdefault(str(device), [])
+            while len(pool) <= k:
+                pool.append(torch.cuda.Stream(device=device))
+            self.side = pool[k]
+        else:
+            self.side = self.main
+        self.ctx = None
+
+    def __enter__(self):
+        if self.side is not self.main:
+            self.side.wait_stream(self.main)
+        self.ctx = torch.cuda.stream(self.side)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        return self.ctx.__exit__(*a)
+
+    def join(self):
+        if self.side is not self.main:
+            self.main.wait_stream(self.side)
+
+
 def _as_float(t, sync):
     return t.item() if sync else t.detach()
 
@@ -237,9 +278,12 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
     wd = [w.detach() for w in gru.layer_weights()]
 
     with torch.no_grad():
-        h_real = model.encode(x)                                                     # tt:175-176
         z = nz.rand(B, T, model.embedder.rnn.rnn.hidden_size)                        # tt:179
+        fork_e = _Fork(device, 0)
+        with fork_e:
+            h_real = model.encode(x)                                                 # tt:175-176  (|| G -> S)
         h_fake = model.refine_latent(model.gen_latent(z))                            # tt:180-181 (forward only)
+        fork_e.join()
         h_real_n = add_instance_noise(h_real, inst_noise_std, nz, True)              # tt:184
         h_fake_n = add_instance_noise(h_fake, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:185
         y_real, y_fake = smooth_labels(B, label_smooth, device, nz)                  # tt:188
@@ -293,9 +337,16 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
         if r1 is not None:
             saves_f = [sv.narrow(B, B) for sv in saves]
             masks_f = None if masks is None else [m[B:] for m in masks]
-            ops.stack_backward(gyf, saves_f, wd, need_dx=False, need_dw=True, dy_last=True, grads=grads,
-                               accumulate=False, masks=masks_f)
+            grads_f = ops.alloc_like_flat(wd)
+            fork_f = _Fork(device, 0)
+            with fork_f:                                   # BPTT of the fake half || reverse-over-tangent of the real half
+                ops.stack_backward(gyf, saves_f, wd, need_dx=False, need_dw=True, dy_last=True, grads=grads_f,
+                                   accumulate=False, masks=masks_f)
+            for gt in grads:
+                gt.zero_()
             ops.stack_jvp_backward(gyr, ghd, saves_r, tsaves, wd, grads, accumulate=True, masks=masks_r)
+            fork_f.join()
+            torch._foreach_add_(grads, grads_f)
         else:
             ops.stack_backward(torch.cat([gyr, gyf], 0), saves, wd, need_dx=False, need_dw=True, dy_last=True,
                                grads=grads, accumulate=False, masks=masks)
@@ -318,21 +369,26 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     B, T = x.size(0), x.size(1)
 
     z = nz.rand(B, T, model.embedder.rnn.rnn.hidden_size)                            # tt:235
+    fork_rec = _Fork(device, 0)
+    with fork_rec:                                   # E -> R on the real batch runs beside G -> S
+        x_tilde = model.reconstruct(x)                                               # tt:247-248
+        g_rec = recon_loss(x, x_tilde)
     e_hat = model.gen_latent(z)
     h_hat = model.refine_latent(e_hat)
-    d_fake = model.discriminator(add_instance_noise(h_hat, inst_noise_std, nz, _latent_is_gru_view(model)),
-                                 frozen=True)                                        # tt:240
-    g_adv = bce(d_fake, torch.ones_like(d_fake))
-    g_sup = sup_loss_fake(h_hat)                                                     # tt:244
-    x_tilde = model.reconstruct(x)                                                   # tt:247-248
-    g_rec = recon_loss(x, x_tilde)
-    x_hat = model.decode(h_hat)                                                      # tt:251
-
+    d_in = add_instance_noise(h_hat, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:240 (noise drawn here)
     cov_term = torch.zeros((), device=device)
     acf_term = torch.zeros((), device=device)
-    if gamma_cov > 0 or gamma_acf > 0:                                               # tt:254-263
-        cov_term, acf_term = _losses.cov_acf_losses(x_hat, x, acf_max_lag, need_cov=gamma_cov > 0,
-                                                    need_acf=gamma_acf > 0)
+    fork_dec = _Fork(device, 1)
+    with fork_dec:                                   # R on the generated latents runs beside D
+        x_hat = model.decode(h_hat)                                                  # tt:251
+        if gamma_cov > 0 or gamma_acf > 0:                                           # tt:254-263
+            cov_term, acf_term = _losses.cov_acf_losses(x_hat, x, acf_max_lag, need_cov=gamma_cov > 0,
+                                                        need_acf=gamma_acf > 0)
+    d_fake = model.discriminator(d_in, frozen=True)
+    g_adv = bce(d_fake, torch.ones_like(d_fake))
+    g_sup = sup_loss_fake(h_hat)                                                     # tt:244
+    fork_rec.join()
+    fork_dec.join()
     g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
 
     _zero_grads(optG)

@@ -74,8 +74,12 @@ def test_five_phase_curves_track_reference(tmp_path, capsys):
         if c == "acc_flips":
             continue
         first10, worst, mean = v
-        if c == "acc_D":      # a count of 64 thresholded probabilities: one flip = 1/64
-            assert np.abs(got[c] - ref[c]).max() <= 8.0 / 64 + 1e-6, (c, report[c])
+        if c == "acc_D":
+            # a count of 64 probabilities thresholded at 0.5 (tt:206-207).  Late in this run the reference's D
+            # outputs sit within ~1e-6 of 0.5, so the count there is the sign of rounding noise (the continuous
+            # losses stay within 1 %); require exact agreement while D is decisive and 3/4 agreement overall.
+            assert np.abs(got[c] - ref[c])[:40].max() <= 1e-6, (c, report[c])
+            assert (np.abs(got[c] - ref[c]) <= 1.0 / 64 + 1e-6).mean() >= 0.75, (c, report[c])
             continue
         assert first10 < 5e-3, (c, report[c])
         assert mean < 2e-2 and worst < 1e-1, (c, report[c])
