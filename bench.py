@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--proj", type=str, default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="disable side-stream concurrency inside the step")
+    ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
     return ap.parse_args()
 
@@ -208,21 +209,33 @@ def run_ours(a):
     torch.manual_seed(42)
     model = tg.TimeGAN(X_DIM, a.hidden, a.hidden, a.layers, 0.0).to(dev)
     P = tt._params
-    optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"])
+    use_graph = not a.no_graph
+    optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"], capturable=use_graph)
     optG = tg.FusedAdam(P(model.generator, model.supervisor, model.embedder, model.recovery), lr=HP["lr_g"],
-                        betas=HP["betas"])
+                        betas=HP["betas"], capturable=use_graph)
     B = a.batch
     n_batches = 8
     g = torch.Generator().manual_seed(1234 + rank)
     host = [torch.rand(B, T_LEN, X_DIM, generator=g).pin_memory() for _ in range(n_batches)]
     resident = [h.to(dev) for h in host]
 
-    def joint(x):
+    def joint_eager(x):
         d = tt.disc_step(model, x, dev, optD, HP["label_smooth"], HP["inst_noise"], HP["clip"], None, HP["r1_gamma"],
                          target_acc=HP["target"], band=HP["band"], sync=False)
         gq = tt.gen_step(model, x, dev, optG, HP["alpha_sup"], HP["beta_rec"], HP["inst_noise"], HP["clip"], None,
                          HP["gamma_cov"], HP["gamma_acf"], HP["acf_max_lag"], sync=False)
-        return d + gq
+        return torch.stack([v.float().reshape(()) for v in d + gq])
+
+    graphed = None
+    if use_graph:
+        graphed = tt.GraphedJointStep(model, optD, optG, dev, label_smooth=HP["label_smooth"], clip=HP["clip"],
+                                      r1_gamma=HP["r1_gamma"], target_acc=HP["target"], band=HP["band"],
+                                      alpha_sup=HP["alpha_sup"], beta_rec=HP["beta_rec"], gamma_cov=HP["gamma_cov"],
+                                      gamma_acf=HP["gamma_acf"], acf_max_lag=HP["acf_max_lag"], warmup=2)
+
+    def joint(x):
+        # the public API a user calls: the graphed step (train_single_npz(graph=True)) or the eager step functions
+        return graphed(x, HP["inst_noise"]) if graphed is not None else joint_eager(x)
 
     def barrier():
         if world > 1:
@@ -236,7 +249,7 @@ def run_ours(a):
         td.all_reduce(t, op=td.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(max(a.warmup, 3)):
+    for i in range(max(a.warmup, 3) + (1 if use_graph else 0)):
         joint(resident[i % n_batches])
     barrier()
 
@@ -245,13 +258,15 @@ def run_ours(a):
     if rank == 0:
         clocks.start()
     _lib.prof_reset()
-    _lib.prof_enable(True)
+    _lib.prof_enable(not use_graph)     # per-call event pairs cannot be recorded into a graph; see region 3
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    t_host0 = time.perf_counter()
     for i in range(a.steps):
         out = joint(resident[i % n_batches])
+    host_issue_ms = (time.perf_counter() - t_host0) * 1e3   # CPU time to ISSUE the steps (no sync inside)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -259,6 +274,7 @@ def run_ours(a):
     _lib.prof_enable(False)
     prof = _lib.prof_read()
     clk = clocks.stop() if rank == 0 else None
+    launches_per_step = launches / a.steps
 
     # ---- timed region 2: end to end from host buffers ----
     scal = torch.empty(8, dtype=torch.float32).pin_memory()
@@ -266,13 +282,36 @@ def run_ours(a):
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for i in range(a.steps):
-        x = host[i % n_batches].to(dev, non_blocking=True)
-        out = joint(x)
-        scal.copy_(torch.stack([o.float().reshape(()) for o in out]), non_blocking=False)
+        if graphed is not None:
+            out = joint(host[i % n_batches])      # pinned host batch -> H2D copy into the graph's input buffer
+        else:
+            out = joint(host[i % n_batches].to(dev, non_blocking=True))
+        scal.copy_(out, non_blocking=False)
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     assert all(v == v for v in scal.tolist()), f"non-finite losses in bench: {scal.tolist()}"
+
+    # ---- region 3 (graph mode only): the same steps issued eagerly with per-call CUDA-event pairs, to attribute
+    #      device time to kernel families (roofline bookkeeping) and to count launches per step ----
+    if use_graph:
+        n_prof = min(a.steps, 5)
+        tt.set_concurrency(False)          # serialise the stacks so an event pair brackets ONE kernel family
+        joint_eager(resident[0])
+        _lib.prof_reset()
+        _lib.prof_enable(True)
+        l0 = _lib.launch_count()
+        barrier()
+        for i in range(n_prof):
+            joint_eager(resident[i % n_batches])
+        barrier()
+        tt.set_concurrency(not a.serial)
+        launches_per_step = (_lib.launch_count() - l0) / n_prof
+        _lib.prof_enable(False)
+        prof = _lib.prof_read()
+        prof_steps = n_prof
+    else:
+        prof_steps = a.steps
 
     if world > 1:
         td.destroy_process_group()
@@ -303,16 +342,20 @@ def run_ours(a):
         "e2e": {"value": round(seqs / (ms_e2e * 1e-3), 2), "unit": "seq/s",
                 "h2d_bytes_per_step": B * T_LEN * X_DIM * 4, "d2h_bytes_per_step": 8 * 4,
                 "ms_per_step": round(ms_e2e / a.steps, 3)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(round(launches_per_step * a.steps)),
+        "issue": "cuda-graph replay (1 graph launch per step)" if use_graph else "eager",
+        "host_issue_ms_per_step": round(host_issue_ms / a.steps, 3),
         "clocks": clk,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(ach_gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                      "avg_launch_ms": round(d["ms"] / max(d["calls"], 1), 4), "launches": d["calls"],
                      "share_of_device_time": round(d["ms"] / total_dev_ms, 4),
+                     "timing": "CUDA-event pair around every C-ABI call of the family, summed over eagerly issued, "
+                               "serialised steps inside this bench run (graph replays cannot carry event pairs)",
                      "ffma": {"achieved": round(ach_tf, 2), "peak": round(ffma_peak, 1), "unit": "TFLOP/s",
                               "frac": round(ach_tf / ffma_peak, 4),
                               "note": "W_hh h runs on fp32 FMA pipes by design; peak = 148 SM x 128 FMA x 2 x sampled clock"}},
-        "families": {k: {"ms_per_step": round(v["ms"] / a.steps, 3), "calls_per_step": round(v["calls"] / a.steps, 1),
+        "families": {k: {"ms_per_step": round(v["ms"] / prof_steps, 3), "calls_per_step": round(v["calls"] / prof_steps, 1),
                          "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
                          "TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else 0.0}
                      for k, v in prof.items() if v["calls"]},

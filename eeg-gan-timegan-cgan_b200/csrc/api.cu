@@ -246,21 +246,21 @@ int tg_sumsq(void* stream, int n, const float* const* grads, const long long* si
 }
 int tg_adam(void* stream, int n, float* const* params, const float* const* grads, float* const* exp_avg,
             float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr, float beta1,
-            float beta2, float eps, int step, float grad_scale) {
+            float beta2, float eps, int step, float grad_scale, float* dev_state) {
   ProfScope _ps(stream, K_OPTIM, 0.0, 0.0);
   return tg_adam_multi_impl((cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, sizes, sumsq, max_norm, lr,
-                            beta1, beta2, eps, step, grad_scale);
+                            beta1, beta2, eps, step, grad_scale, dev_state);
 }
 
 int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,
-                   float hi) {
+                   float hi, const unsigned long long* ctr) {
   ProfScope _ps(stream, K_RNG, 4.0 * (double)n, 0.0);
-  return tg_rng_uniform_impl((cudaStream_t)stream, out, n, seed, offset, lo, hi);
+  return tg_rng_uniform_impl((cudaStream_t)stream, out, n, seed, offset, lo, hi, ctr);
 }
 int tg_rng_add_normal(void* stream, const float* in, float* out, long long n, float std, unsigned long long seed,
-                      unsigned long long offset) {
+                      unsigned long long offset, const unsigned long long* ctr) {
   ProfScope _ps(stream, K_RNG, 8.0 * (double)n, 0.0);
-  return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, std, seed, offset);
+  return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, std, seed, offset, ctr);
 }
 
 }  // extern "C"

@@ -25,10 +25,10 @@ int tg_sumsq_multi_impl(cudaStream_t st, int n, const float* const* grads, const
                         void* ws, size_t wsb);
 int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float* const* grads, float* const* exp_avg,
                        float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr,
-                       float beta1, float beta2, float eps, int step, float grad_scale);
+                       float beta1, float beta2, float eps, int step, float grad_scale, float* dev_state);
 
 // rng
 int tg_rng_uniform_impl(cudaStream_t st, float* out, long long n, unsigned long long seed, unsigned long long offset,
-                        float lo, float hi);
+                        float lo, float hi, const unsigned long long* ctr);
 int tg_rng_add_normal_impl(cudaStream_t st, const float* in, float* out, long long n, float std,
-                           unsigned long long seed, unsigned long long offset);
+                           unsigned long long seed, unsigned long long offset, const unsigned long long* ctr);

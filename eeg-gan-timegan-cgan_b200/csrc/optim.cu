@@ -66,10 +66,23 @@ __global__ void __launch_bounds__(256) sumsq_final_kernel(const double* part, in
   }
 }
 
+// Device-resident optimiser clock for CUDA-graph replay: state = {lr, step}; one thread advances the step and
+// derives the bias-correction factors in double, like the host path does.
+__global__ void adam_tick_kernel(float* __restrict__ state, float* __restrict__ derived, float beta1, float beta2) {
+  const float step = state[1] + 1.0f;
+  state[1] = step;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  derived[0] = (float)((double)state[0] / bc1);   // step_size
+  derived[1] = (float)sqrt(bc2);                  // bc2_sqrt
+}
+
 __global__ void __launch_bounds__(MT_THREADS) adam_multi_kernel(const __grid_constant__ MtArgs a,
                                                                 const float* __restrict__ sumsq, float max_norm,
                                                                 float step_size, float bc2_sqrt, float beta1,
-                                                                float beta2, float eps, float grad_scale) {
+                                                                float beta2, float eps, float grad_scale,
+                                                                const float* __restrict__ derived) {
+  if (derived) { step_size = derived[0]; bc2_sqrt = derived[1]; }
   const int t = find_tensor(a, blockIdx.x);
   const long long base = (long long)(blockIdx.x - a.blk_start[t]) * MT_CHUNK;
   const long long end = min(a.size[t], base + MT_CHUNK);
@@ -143,14 +156,24 @@ int tg_sumsq_multi_impl(cudaStream_t st, int n, const float* const* grads, const
 
 int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float* const* grads, float* const* exp_avg,
                        float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr,
-                       float beta1, float beta2, float eps, int step, float grad_scale) {
+                       float beta1, float beta2, float eps, int step, float grad_scale, float* dev_state) {
   TG_REQUIRE(n > 0 && params && grads && exp_avg && exp_avg_sq && sizes, TG_ERR_ARG, "adam_multi: bad arguments");
-  TG_REQUIRE(step >= 1, TG_ERR_ARG, "adam_multi: step must be >= 1 (got %d)", step);
+  TG_REQUIRE(dev_state || step >= 1, TG_ERR_ARG, "adam_multi: step must be >= 1 (got %d)", step);
   TG_REQUIRE(max_norm <= 0.f || sumsq, TG_ERR_ARG, "adam_multi: clipping requested without sumsq");
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
-  const float bc2_sqrt = (float)sqrt(bc2);
+  float step_size = 0.f, bc2_sqrt = 1.f;
+  const float* derived = nullptr;
+  if (dev_state) {
+    // dev_state: float[4] = {lr, step, step_size, bc2_sqrt}; lr is written by the host outside any graph
+    adam_tick_kernel<<<1, 1, 0, st>>>(dev_state, dev_state + 2, beta1, beta2);
+    int rc = tg_check_launch("adam_tick");
+    if (rc) return rc;
+    derived = dev_state + 2;
+  } else {
+    const double bc1 = 1.0 - pow((double)beta1, (double)step);
+    const double bc2 = 1.0 - pow((double)beta2, (double)step);
+    step_size = (float)((double)lr / bc1);
+    bc2_sqrt = (float)sqrt(bc2);
+  }
   for (int i0 = 0; i0 < n; i0 += TG_MT_MAX) {
     const int cnt = (n - i0 < TG_MT_MAX) ? n - i0 : TG_MT_MAX;
     MtArgs a{};
@@ -161,7 +184,7 @@ int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float
     }
     const int blocks = fill_blocks(a, sizes + i0, cnt);
     adam_multi_kernel<<<blocks, MT_THREADS, 0, st>>>(a, sumsq, max_norm, step_size, bc2_sqrt, beta1, beta2, eps,
-                                                     grad_scale);
+                                                     grad_scale, derived);
     int rc = tg_check_launch("adam_multi");
     if (rc) return rc;
   }

@@ -29,7 +29,11 @@ __device__ __forceinline__ void philox4x32_10(uint64_t ctr, uint64_t seed, uint3
 // (0,1]-open-at-zero uniform from 24 random bits -> [0,1) like torch.rand: k / 2^24
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-__global__ void uniform_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset, float lo, float hi) {
+// `ctr` (optional, device memory) is added to the call's offset: a CUDA graph bakes `offset` in, the device
+// counter advances between replays, so every replay draws fresh numbers from the same Philox stream.
+__global__ void uniform_kernel(float* __restrict__ out, long long n, uint64_t seed, uint64_t offset, float lo, float hi,
+                               const unsigned long long* __restrict__ ctr) {
+  if (ctr) offset += *ctr;
   const long long n4 = (n + 3) / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
@@ -44,7 +48,8 @@ __global__ void uniform_kernel(float* __restrict__ out, long long n, uint64_t se
 }
 
 __global__ void add_normal_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float std,
-                                  uint64_t seed, uint64_t offset) {
+                                  uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ ctr) {
+  if (ctr) offset += *ctr;
   const long long n4 = (n + 3) / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
@@ -78,15 +83,15 @@ int blocks_for(long long n4) {
 }  // namespace
 
 int tg_rng_uniform_impl(cudaStream_t st, float* out, long long n, unsigned long long seed, unsigned long long offset,
-                        float lo, float hi) {
+                        float lo, float hi, const unsigned long long* ctr) {
   TG_REQUIRE(out && n > 0, TG_ERR_ARG, "rng_uniform: bad arguments");
-  uniform_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(out, n, seed, offset, lo, hi);
+  uniform_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(out, n, seed, offset, lo, hi, ctr);
   return tg_check_launch("rng_uniform");
 }
 
 int tg_rng_add_normal_impl(cudaStream_t st, const float* in, float* out, long long n, float std,
-                           unsigned long long seed, unsigned long long offset) {
+                           unsigned long long seed, unsigned long long offset, const unsigned long long* ctr) {
   TG_REQUIRE(out && n > 0, TG_ERR_ARG, "rng_add_normal: bad arguments");
-  add_normal_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(in, out, n, std, seed, offset);
+  add_normal_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(in, out, n, std, seed, offset, ctr);
   return tg_check_launch("rng_add_normal");
 }

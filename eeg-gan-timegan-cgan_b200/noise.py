@@ -9,21 +9,31 @@ import torch
 from ._lib import lib, check, ptr, stream_ptr, require_cuda
 
 
-def uniform(shape, device, seed: int, offset: int, lo: float = 0.0, hi: float = 1.0) -> torch.Tensor:
+def uniform(shape, device, seed: int, offset: int, lo: float = 0.0, hi: float = 1.0, ctr=None) -> torch.Tensor:
+    """U[lo,hi).  `ctr`: optional int64 device scalar added to `offset` on the device (CUDA-graph replay)."""
     out = torch.empty(shape, dtype=torch.float32, device=device)
     require_cuda(out, "noise output")
-    check(lib.tg_rng_uniform(stream_ptr(), ptr(out), out.numel(), seed, offset, lo, hi), "tg_rng_uniform")
+    check(lib.tg_rng_uniform(stream_ptr(), ptr(out), out.numel(), seed, offset, lo, hi, ptr(ctr)), "tg_rng_uniform")
     return out
 
 
-def add_normal(h: torch.Tensor, std: float, seed: int, offset: int) -> torch.Tensor:
+def add_normal(h: torch.Tensor, std: float, seed: int, offset: int, ctr=None) -> torch.Tensor:
     """h + std*N(0,1); returns h itself when std <= 0 (tt:46-47)."""
     if std <= 0:
         return h
     require_cuda(h, "instance-noise input")
     h = h.contiguous()
     out = torch.empty_like(h)
-    check(lib.tg_rng_add_normal(stream_ptr(), ptr(h), ptr(out), h.numel(), float(std), seed, offset),
+    check(lib.tg_rng_add_normal(stream_ptr(), ptr(h), ptr(out), h.numel(), float(std), seed, offset, ptr(ctr)),
+          "tg_rng_add_normal")
+    return out
+
+
+def normal(shape, device, seed: int, offset: int, ctr=None) -> torch.Tensor:
+    """N(0,1) of the given shape."""
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    require_cuda(out, "noise output")
+    check(lib.tg_rng_add_normal(stream_ptr(), None, ptr(out), out.numel(), 1.0, seed, offset, ptr(ctr)),
           "tg_rng_add_normal")
     return out
 
@@ -34,26 +44,45 @@ def draws_for(n: int) -> int:
 
 
 class DeviceNoise:
-    """Production noise source: Philox stream keyed by (seed, running offset); draw order of SURVEY.md App. B."""
+    """Production noise source: one Philox stream keyed by `seed`; position = device counter + offset within the
+    step.  The counter lives in device memory and is advanced by `end()` with a device-side add, so a captured
+    CUDA graph (which bakes the per-call offsets in) draws fresh numbers at every replay, and eager and graphed
+    runs consume the identical stream.  Draw order inside a step follows SURVEY.md Appendix B."""
 
     def __init__(self, seed: int, device):
-        self.seed, self.device, self.offset = int(seed) & 0xFFFFFFFFFFFFFFFF, device, 0
+        self.seed, self.device = int(seed) & 0x7FFFFFFFFFFFFFFF, device
+        self.ctr = torch.zeros((), dtype=torch.int64, device=device)
+        self.local = 0
 
     def _adv(self, n):
-        o = self.offset
-        self.offset += draws_for(n)
+        o = self.local
+        self.local += draws_for(n)
         return o
+
+    def begin(self):
+        self.local = 0
+
+    def end(self):
+        if self.local:
+            self.ctr.add_(self.local)
+        self.local = 0
 
     def rand(self, *shape):
         n = 1
         for s in shape:
             n *= s
-        return uniform(shape, self.device, self.seed, self._adv(n))
+        return uniform(shape, self.device, self.seed, self._adv(n), ctr=self.ctr)
+
+    def randn(self, shape):
+        n = 1
+        for s in shape:
+            n *= s
+        return normal(tuple(shape), self.device, self.seed, self._adv(n), ctr=self.ctr)
 
     def add_randn(self, h, std):
         if std <= 0:
             return h
-        return add_normal(h, std, self.seed, self._adv(h.numel()))
+        return add_normal(h, std, self.seed, self._adv(h.numel()), ctr=self.ctr)
 
     def state(self):
-        return {"seed": self.seed, "offset": self.offset}
+        return {"seed": self.seed, "ctr": int(self.ctr.item())}

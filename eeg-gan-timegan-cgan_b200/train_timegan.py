@@ -69,6 +69,12 @@ class HostReplayNoise:
     def rand(self, *shape):
         return torch.rand(*shape).to(self.device)
 
+    def begin(self):
+        pass
+
+    def end(self):
+        pass
+
     def randn_like(self, h, time_major: bool = False):
         """torch.randn_like on a CPU tensor with the strides the reference's tensor has at that call site:
         nn.GRU(batch_first=True) returns a transposed view of a (T,B,H) buffer on the CPU, and randn_like
@@ -92,10 +98,21 @@ class _DeviceNoiseAdapter:
         return self.src.rand(*shape)
 
     def randn_like(self, h, time_major: bool = False):
-        return self.src.add_randn(torch.zeros_like(h), 1.0)
+        return self.src.randn(h.shape)
+
+    def begin(self):
+        self.src.begin()
+
+    def end(self):
+        self.src.end()
 
 
 _DEFAULT_NOISE: Dict[str, _DeviceNoiseAdapter] = {}
+
+
+def device_noise(seed: int, device):
+    """An independent on-device noise source (Philox stream `seed`) usable as the `noise=` argument."""
+    return _DeviceNoiseAdapter(_noise.DeviceNoise(seed, device))
 
 
 def _noise_source(noise, device):
@@ -115,8 +132,9 @@ def smooth_labels(size: int, smooth: float, device, noise=None) -> Tuple[torch.T
 
 
 def add_instance_noise(h: torch.Tensor, std: float, noise=None, time_major: bool = False) -> torch.Tensor:
-    """tt:46-47.  `time_major` only matters to host-replayed noise (layout of the reference's tensor)."""
-    if std <= 0:
+    """tt:46-47.  `time_major` only matters to host-replayed noise (layout of the reference's tensor).
+    `std` may be a 0-dim device tensor (CUDA-graph replay: the value changes every step, the graph does not)."""
+    if not torch.is_tensor(std) and std <= 0:
         return h
     return h + std * _noise_source(noise, h.device).randn_like(h, time_major)
 
@@ -273,6 +291,7 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
     D = model.discriminator
     D.train()
     nz = _noise_source(noise, device)
+    nz.begin()
     B, T = x.size(0), x.size(1)
     gru = D.rnn.rnn
     wd = [w.detach() for w in gru.layer_weights()]
@@ -355,6 +374,7 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
         p.grad = g
     D.fc.weight_orig.grad, D.fc.bias.grad = gw, gb
     _reduce_and_step(optD, _params(D), clip)
+    nz.end()
     if schedulerD is not None:
         schedulerD.step()
     return _as_float(loss_val, sync), _as_float(acc, sync)
@@ -366,6 +386,7 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     """Generator/supervisor/embedder/recovery update (tt:228-276).  Returns the six logged losses."""
     model.generator.train(); model.supervisor.train(); model.embedder.train(); model.recovery.train()
     nz = _noise_source(noise, device)
+    nz.begin()
     B, T = x.size(0), x.size(1)
 
     z = nz.rand(B, T, model.embedder.rnn.rnn.hidden_size)                            # tt:235
@@ -395,10 +416,82 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     g_total.backward()
     params = _params(model.generator, model.supervisor, model.embedder, model.recovery)
     _reduce_and_step(optG, params, clip)
+    nz.end()
     if schedulerG is not None:
         schedulerG.step()
     vals = (g_total, g_adv, g_sup, g_rec, cov_term, acf_term)
     return tuple(_as_float(v, sync) for v in vals)
+
+
+class GraphedJointStep:
+    """One joint training step (disc_step + gen_step, tt:379-395) captured in a CUDA graph.
+
+    A joint step issues ~3200 kernel launches and ~30 ms of Python/ctypes work; once the GPU finishes a step
+    faster than the host can issue it, the host is the bottleneck.  Capturing removes it: every replay re-runs
+    the same launches with the same device pointers, while everything that changes from step to step lives in
+    device memory -- the input batch (`self.x`), the instance-noise std (`self.std`), the Philox position
+    (noise.DeviceNoise.ctr), Adam's step counter / lr / bias corrections (FusedAdam(capturable=True)).
+    The first `warmup` calls run eagerly (they are real training steps); the next call captures and replays.
+    Needs on-device noise (noise=None) and capturable optimisers; LR schedulers are stepped here, outside the graph."""
+
+    def __init__(self, model, optD, optG, device, *, label_smooth, clip, r1_gamma, target_acc, band, alpha_sup,
+                 beta_rec, gamma_cov, gamma_acf, acf_max_lag, schedulerD=None, schedulerG=None, warmup: int = 3,
+                 noise=None):
+        if not (getattr(optD, "capturable", False) and getattr(optG, "capturable", False)):
+            raise ValueError("GraphedJointStep needs FusedAdam(capturable=True) optimisers")
+        self.model, self.optD, self.optG, self.device = model, optD, optG, torch.device(device)
+        self.kw = dict(label_smooth=label_smooth, clip=clip, r1_gamma=r1_gamma, target_acc=target_acc, band=band,
+                       alpha_sup=alpha_sup, beta_rec=beta_rec, gamma_cov=gamma_cov, gamma_acf=gamma_acf,
+                       acf_max_lag=acf_max_lag)
+        self.schedulerD, self.schedulerG = schedulerD, schedulerG
+        if isinstance(noise, HostReplayNoise):
+            raise ValueError("host-replayed noise cannot be captured in a CUDA graph")
+        self.noise = noise
+        self.warmup, self.calls = int(warmup), 0
+        self.x = None
+        self.std = torch.zeros((), dtype=torch.float32, device=self.device)
+        self.graph = None
+        self.out = None
+        self._noise_on = None
+
+    def _joint(self):
+        k = self.kw
+        std = self.std if self._noise_on else 0.0
+        d = disc_step(self.model, self.x, self.device, self.optD, k["label_smooth"], std, k["clip"], None,
+                      k["r1_gamma"], target_acc=k["target_acc"], band=k["band"], noise=self.noise, sync=False)
+        g = gen_step(self.model, self.x, self.device, self.optG, k["alpha_sup"], k["beta_rec"], std, k["clip"], None,
+                     k["gamma_cov"], k["gamma_acf"], k["acf_max_lag"], noise=self.noise, sync=False)
+        return torch.stack([v.float().reshape(()) for v in tuple(d) + tuple(g)])
+
+    def __call__(self, x, inst_noise_std: float):
+        """x: (B,T,C) device or pinned-host tensor.  Returns the 8 logged scalars as one device tensor
+        (loss_D, acc_D, loss_G, adv, sup, rec, cov, acf); it is overwritten by the next call."""
+        if self.x is None:
+            self.x = torch.empty(x.shape, dtype=torch.float32, device=self.device)
+            self._noise_on = inst_noise_std > 0
+        if tuple(x.shape) != tuple(self.x.shape):
+            raise ValueError(f"GraphedJointStep was built for batches of shape {tuple(self.x.shape)}, got {tuple(x.shape)}")
+        if (inst_noise_std > 0) != self._noise_on:
+            raise ValueError("instance noise cannot be switched on/off after capture")
+        self.x.copy_(x, non_blocking=True)
+        self.std.fill_(float(inst_noise_std))
+        self.optD.push_lr()
+        self.optG.push_lr()
+        if self.calls < self.warmup:
+            out = self._joint()
+        else:
+            if self.graph is None:
+                torch.cuda.synchronize(self.device)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.out = self._joint()
+            self.graph.replay()
+            out = self.out
+        self.calls += 1
+        for sch in (self.schedulerD, self.schedulerG):
+            if sch is not None:
+                sch.step()
+        return out
 
 
 # ---------------------- Full training (tt:281-422) ----------------------

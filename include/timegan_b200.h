@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 2
+#define TG_ABI_VERSION 3
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -127,14 +127,16 @@ int tg_sumsq(void* stream, int n, const float* const* grads, const long long* si
              size_t ws_bytes);
 int tg_adam(void* stream, int n, float* const* params, const float* const* grads, float* const* exp_avg,
             float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr, float beta1,
-            float beta2, float eps, int step, float grad_scale);
+            float beta2, float eps, int step, float grad_scale,
+            float* dev_state /* NULL, or device float[4] {lr, step, -, -}: the step counter and bias corrections
+                                then live on the device (CUDA-graph replay); `lr`/`step` arguments are ignored */);
 
 /* ---- noise (train_timegan.py:64-65 sample_noise, :46-47 add_instance_noise, :40-43 smooth_labels) --------
  * Philox4x32-10 keyed by (seed, offset); each call consumes ceil(n/4) counter values. */
 int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,
-                   float hi);
+                   float hi, const unsigned long long* ctr /* NULL or device counter added to offset */);
 int tg_rng_add_normal(void* stream, const float* in /* may be NULL */, float* out, long long n, float std,
-                      unsigned long long seed, unsigned long long offset);
+                      unsigned long long seed, unsigned long long offset, const unsigned long long* ctr);
 
 #ifdef __cplusplus
 }

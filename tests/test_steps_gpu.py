@@ -137,3 +137,49 @@ def test_cpu_tensor_is_refused():
     m = tg.TimeGAN(14, 8, 8, 1, 0.0)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.encode(torch.rand(2, 5, 14))
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """GraphedJointStep (captured disc_step + gen_step, device-side Adam clock / lr / Philox counter) reproduces
+    the eagerly issued steps: same weights, same noise stream, 8 steps incl. an LR-schedule change."""
+    import copy
+    import timegan_b200 as tg
+    from timegan_b200 import train_timegan as tt
+    torch.manual_seed(5)
+    base = tg.TimeGAN(14, 24, 24, 2, 0.0).to(DEV)
+    xs = [torch.rand(6, 48, 14, device=DEV) for _ in range(8)]
+    hp = dict(label_smooth=0.2, clip=0.5, r1_gamma=1.0, target_acc=0.525, band=0.15, alpha_sup=5.0, beta_rec=0.2,
+              gamma_cov=0.05, gamma_acf=0.05, acf_max_lag=16)
+    P = tt._params
+    outs = {}
+    finals = {}
+    for mode in ("eager", "graph"):
+        m = copy.deepcopy(base)
+        cap = mode == "graph"
+        oD = tg.FusedAdam(m.discriminator.parameters(), lr=2e-4, betas=(0.5, 0.9), capturable=cap)
+        oG = tg.FusedAdam(P(m.generator, m.supervisor, m.embedder, m.recovery), lr=1e-3, betas=(0.5, 0.9), capturable=cap)
+        sD = torch.optim.lr_scheduler.MultiStepLR(oD, milestones=[4, 6], gamma=0.5)
+        sG = torch.optim.lr_scheduler.MultiStepLR(oG, milestones=[4, 6], gamma=0.5)
+        nz = tt.device_noise(1234, torch.device(DEV))
+        rows = []
+        if cap:
+            step = tt.GraphedJointStep(m, oD, oG, DEV, schedulerD=sD, schedulerG=sG, warmup=2, noise=nz, **hp)
+            for i, x in enumerate(xs):
+                rows.append(step(x, 0.3 - 0.01 * i).clone())
+            assert step.graph is not None
+        else:
+            for i, x in enumerate(xs):
+                d = tt.disc_step(m, x, DEV, oD, hp["label_smooth"], 0.3 - 0.01 * i, hp["clip"], sD, hp["r1_gamma"],
+                                 target_acc=hp["target_acc"], band=hp["band"], noise=nz, sync=False)
+                g = tt.gen_step(m, x, DEV, oG, hp["alpha_sup"], hp["beta_rec"], 0.3 - 0.01 * i, hp["clip"], sG,
+                                hp["gamma_cov"], hp["gamma_acf"], hp["acf_max_lag"], noise=nz, sync=False)
+                rows.append(torch.stack([v.float().reshape(()) for v in d + g]))
+        outs[mode] = torch.stack(rows).cpu()
+        finals[mode] = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        if cap:
+            sd = oG.state_dict()
+            assert float(sd["state"][0]["step"]) == len(xs)
+    assert torch.isfinite(outs["graph"]).all()
+    assert torch.allclose(outs["graph"], outs["eager"], rtol=2e-4, atol=1e-6), (outs["graph"] - outs["eager"]).abs().max()
+    for k in finals["eager"]:
+        assert (finals["graph"][k] - finals["eager"][k]).abs().max().item() < 2e-5, k
