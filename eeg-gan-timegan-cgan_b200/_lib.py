@@ -41,6 +41,8 @@ SIGNATURES = {
     "tg_dgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i]),
     "tg_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
     "tg_wgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _i]),
+    "tg_wgrad_gru_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "tg_wgrad_gru": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _i]),
     "tg_gru_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "tg_gru_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "tg_gru_jvp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),

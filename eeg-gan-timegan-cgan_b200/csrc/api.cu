@@ -168,6 +168,39 @@ int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, fl
                        ws_bytes);
 }
 
+size_t tg_wgrad_gru_workspace_bytes(int B, int T, int I, int H) {
+  const int M = B * T;
+  size_t need = tg_wgrad_gru_ws_bytes(M, I, H);
+  const size_t a = tg_wgrad_workspace_bytes(M, 3 * H, I > 0 ? I : 1), b = tg_wgrad_workspace_bytes(M, 2 * H, H),
+               c = tg_wgrad_workspace_bytes(M, H, H);
+  if (a > need) need = a;
+  if (b > need) need = b;
+  if (c > need) need = c;
+  return need;
+}
+
+int tg_wgrad_gru(void* stream, const float* dgi, const float* dq, const float* x, int ldx, const float* y, float* dW_ih,
+                 float* dW_hh, float* db_ih, float* db_hh, int B, int T, int I, int H, int accumulate, void* ws,
+                 size_t ws_bytes, int mode) {
+  const int M = B * T;
+  if (mode == TG_PROJ_BF16 || mode == TG_PROJ_TF32X3) {
+    ProfScope _ps(stream, K_WGRAD, 4.0 * M * (4.0 * H + (x ? I : 0) + H), 2.0 * M * 3.0 * H * ((x ? I : 0) + H));
+    int rc = tg_wgrad_gru_tc_impl((cudaStream_t)stream, dgi, dq, x, ldx, y, dW_ih, dW_hh, db_ih, db_hh, B, T, I, H,
+                                  accumulate, (float*)ws, ws_bytes, mode == TG_PROJ_TF32X3 ? 3 : 1);
+    if (rc != TG_ERR_UNSUPPORTED) return rc;
+  }
+  // shapes the fused tile cannot take: the three contractions one by one (each picks its own best kernel)
+  int rc = 0;
+  if (x) {
+    rc = tg_wgrad(stream, dgi, 3 * H, x, ldx, dW_ih, I, db_ih, M, 3 * H, I, 0, accumulate, ws, ws_bytes, mode);
+    if (rc) return rc;
+  }
+  rc = tg_wgrad(stream, dgi, 3 * H, y, H, dW_hh, H, db_hh, M, 2 * H, H, T, accumulate, ws, ws_bytes, mode);
+  if (rc) return rc;
+  return tg_wgrad(stream, dq, H, y, H, dW_hh + (size_t)2 * H * H, H, db_hh ? db_hh + 2 * H : nullptr, M, H, H, T,
+                  accumulate, ws, ws_bytes, mode);
+}
+
 int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, float* y, float* q, int B, int T, int H,
                int flags) {
   ProfScope _ps(stream, K_GRU_FWD, (double)B * T * H * ((flags & TG_GRU_SAVE) ? 32.0 : 16.0), 6.0 * B * T * (double)H * H);

@@ -40,6 +40,10 @@ size_t tg_wgrad_tc_ws_bytes(int M, int N, int K);
 int tg_wgrad_tc_impl(cudaStream_t st, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw,
                      float* db, int M, int N, int K, int a_shift_T, int accumulate, float* ws, size_t ws_bytes,
                      int passes);
+size_t tg_wgrad_gru_ws_bytes(int M, int I, int H);
+int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, const float* x, int ldx, const float* y,
+                         float* dW_ih, float* dW_hh, float* db_ih, float* db_hh, int B, int T, int I, int H,
+                         int accumulate, float* ws, size_t ws_bytes, int passes);
 int tg_max_optin_smem();
 
 // column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)

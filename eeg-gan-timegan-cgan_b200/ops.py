@@ -116,6 +116,21 @@ def wgrad(dg2d: torch.Tensor, a2d: torch.Tensor, dw: torch.Tensor, db: Optional[
                        _PROJ_MODE if mode is None else mode), "tg_wgrad")
 
 
+def wgrad_gru(dgi: torch.Tensor, dq: torch.Tensor, x2d: Optional[torch.Tensor], y: torch.Tensor, g_wih, g_whh,
+              g_bih, g_bhh, accumulate: bool = False, mode: Optional[int] = None):
+    """All weight gradients of one GRU layer from the BPTT outputs dgi (B,T,3H), dq (B,T,H), the layer input
+    x2d (B*T,I) (None: skip dW_ih) and the layer output y (B,T,H).  Biases may be None (tangent path)."""
+    B, T, H = y.shape
+    I = x2d.shape[1] if x2d is not None else 0
+    if x2d is not None and (x2d.stride(1) != 1):
+        x2d = x2d.contiguous()
+    nbytes = lib.tg_wgrad_gru_workspace_bytes(B, T, max(I, 1), H)
+    ws = _ws(nbytes, y.device)
+    check(lib.tg_wgrad_gru(stream_ptr(), ptr(dgi), ptr(dq), ptr(x2d), x2d.stride(0) if x2d is not None else 0, ptr(y),
+                           ptr(g_wih) if x2d is not None else None, ptr(g_whh), ptr(g_bih), ptr(g_bhh), B, T, I, H,
+                           int(accumulate), ptr(ws), nbytes, _PROJ_MODE if mode is None else mode), "tg_wgrad_gru")
+
+
 def colsum(x2d: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     M, N = x2d.shape
     if out is None:
@@ -192,10 +207,7 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
         dgi2 = dgi.view(B * T, 3 * H)
         if need_dw:
             g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
-            wgrad(dgi2, sv.inp.view(B * T, I), g_wih, g_bih, 3 * H, 0, accumulate)
-            y2 = sv.y.view(B * T, H)
-            wgrad(dgi2, y2, g_whh[: 2 * H], g_bhh[: 2 * H], 2 * H, T, accumulate)
-            wgrad(dq.view(B * T, H), y2, g_whh[2 * H:], g_bhh[2 * H:], H, T, accumulate)
+            wgrad_gru(dgi, dq, sv.inp.reshape(B * T, I), sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
         if l > 0 or need_dx:
             dx = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             dgrad(dgi2, w_ih, dx.view(B * T, I))
@@ -266,13 +278,9 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
         gib2, gidb2 = gib.view(B * T, 3 * H), gidb.view(B * T, 3 * H)
         y2, yd2 = sv.y.view(B * T, H), ts.ydot.view(B * T, H)
         # primal path
-        wgrad(gib2, sv.inp.view(B * T, I), g_wih, g_bih, 3 * H, 0, accumulate)
-        wgrad(gib2, y2, g_whh[: 2 * H], g_bhh[: 2 * H], 2 * H, T, accumulate)
-        wgrad(qb.view(B * T, H), y2, g_whh[2 * H:], g_bhh[2 * H:], H, T, accumulate)
+        wgrad_gru(gib, qb, sv.inp.reshape(B * T, I), sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
         # tangent path (no bias terms in the tangent)
-        wgrad(gidb2, ts.xdot.view(B * T, I), g_wih, None, 3 * H, 0, True)
-        wgrad(gidb2, yd2, g_whh[: 2 * H], None, 2 * H, T, True)
-        wgrad(qdb.view(B * T, H), yd2, g_whh[2 * H:], None, H, T, True)
+        wgrad_gru(gidb, qdb, ts.xdot.reshape(B * T, I), ts.ydot, g_wih, g_whh, None, None, True)
         if l > 0:
             hb = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             hdb = torch.empty(B, T, I, dtype=torch.float32, device=dev)

@@ -77,6 +77,15 @@ size_t tg_wgrad_workspace_bytes(int M, int N, int K);
 int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
              int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes, int mode /* TG_PROJ_* */);
 
+/* ---- all weight gradients of one GRU layer in one pass over dGI, dq, x, y:
+ * dW_ih (3H,I) (+)= dGI^T x, db_ih (+)= colsum(dGI), dW_hh (3H,H) (+)= [dGI[:, :2H] | dq]^T h_prev, db_hh likewise,
+ * h_prev = y shifted by one step inside every sequence (zero at t = 0).  dgi (B*T,3H), dq (B*T,H), y (B*T,H)
+ * contiguous; x (B*T,I) with leading dimension ldx, or NULL to skip dW_ih; db_* may be NULL. */
+size_t tg_wgrad_gru_workspace_bytes(int B, int T, int I, int H);
+int tg_wgrad_gru(void* stream, const float* dgi, const float* dq, const float* x, int ldx, const float* y, float* dW_ih,
+                 float* dW_hh, float* db_ih, float* db_hh, int B, int T, int I, int H, int accumulate, void* ws,
+                 size_t ws_bytes, int mode /* TG_PROJ_* */);
+
 /* ---- persistent fused GRU layer forward (timegan_model.py:32-34 -> nn.GRU per-timestep loop) --------------
  * gi (B,T,3H) holds X W_ih^T + b_ih on entry; with TG_GRU_SAVE it holds r,z,n on exit and q (B,T,H) receives
  * h_{t-1} W_hn^T + b_hn.  y (B,T,H) receives h_t.  h0 = 0 (the reference never passes an initial state). */
