@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(HP* G, bwd_min_blocks<HP, G>()) gru_bwd_kernel
   pipe.reverse = true; pipe.bulk = p.bulk != 0;
 
   // W_hh^T slice: wt[g][m] = W_hh[g*H + jj][k], jj = (i*G+ql)*4+c
-  float wt[3][KS];
+  float2 wt[3][KS / 2];   // float2 pairs for packed FFMA2
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(HP* G, bwd_min_blocks<HP, G>()) gru_bwd_kernel
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         int jj = (i * G + ql) * 4 + c;
-        wt[g][4 * i + c] = (k < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + k] : 0.f;
+        const float v = (k < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + k] : 0.f;
+        if (c & 1) wt[g][2 * i + (c >> 1)].y = v; else wt[g][2 * i + (c >> 1)].x = v;
       }
   for (int i = tid; i < 2 * BT * 3 * HR; i += HP * G) dgs[i] = 0.f;
   // carry[o]: dL/dh_t[k] flowing in from step t+1 for the sequence this lane owns (b = o*G + ql, or b = ql)
@@ -122,21 +123,24 @@ __global__ void __launch_bounds__(HP* G, bwd_min_blocks<HP, G>()) gru_bwd_kernel
       if (tl == 0 && pipe.bulk) fence_async_smem();
       __syncthreads();
       // ---- carry_k = dh*z + sum_rows dGH[row] * W_hh[row][k] ----
-      float acc[BT];
+      // three independent packed accumulators per sequence (one per gate) keep the FFMA2 chains short
+      float2 acc2[BT][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc[b] = 0.f;
+      for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int g = 0; g < 3; ++g)
+      for (int i = 0; i < KS / 4; ++i)
 #pragma unroll
-        for (int i = 0; i < KS / 4; ++i)
+        for (int g = 0; g < 3; ++g)
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
             const float4 dv = reinterpret_cast<const float4*>(dg + (b * 3 + g) * HR)[i * G + ql];
-            acc[b] = fmaf(wt[g][4 * i + 0], dv.x, acc[b]);
-            acc[b] = fmaf(wt[g][4 * i + 1], dv.y, acc[b]);
-            acc[b] = fmaf(wt[g][4 * i + 2], dv.z, acc[b]);
-            acc[b] = fmaf(wt[g][4 * i + 3], dv.w, acc[b]);
+            acc2[b][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(dv.x, dv.y), acc2[b][g]);
+            acc2[b][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(dv.z, dv.w), acc2[b][g]);
           }
+      float acc[BT];
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+        acc[b] = (acc2[b][0].x + acc2[b][0].y) + (acc2[b][1].x + acc2[b][1].y) + (acc2[b][2].x + acc2[b][2].y);
       // reduce-scatter over the lane group: the owner of (k, b) receives the complete sum
       if constexpr (BT < G) {
         float mine = 0.f;

@@ -65,7 +65,8 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
   pipe.reverse = false; pipe.bulk = p.bulk != 0;
 
   // ---- W_hh slice into registers (interleaved float4 k-assignment => conflict-free LDS.128 of h) ----
-  float w[3][KS];
+  // stored as float2 pairs: the mat-vec runs on packed FFMA2 (two k values per instruction, sm_100)
+  float2 w[3][KS / 2];
   float bh[3];
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         int k = (i * G + ql) * 4 + c;
-        w[g][4 * i + c] = (j < H && k < H) ? p.whh[(size_t)(g * H + j) * H + k] : 0.f;
+        const float v = (j < H && k < H) ? p.whh[(size_t)(g * H + j) * H + k] : 0.f;
+        if (c & 1) w[g][2 * i + (c >> 1)].y = v; else w[g][2 * i + (c >> 1)].x = v;
       }
   }
   for (int i = tid; i < 2 * BT * HR; i += HP * G) hs[i] = 0.f;
@@ -93,23 +95,27 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
     for (int tl = 0; tl < tcn; ++tl) {
       const float* hc = hs + cur * BT * HR;
       float* hn = hs + (cur ^ 1) * BT * HR;
-      float acc[BT][3];
+      float2 acc2[BT][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
+      for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < KS / 4; ++i) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
           const float4 hv = reinterpret_cast<const float4*>(hc + b * HR)[i * G + ql];
+          const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
-            acc[b][g] = fmaf(w[g][4 * i + 0], hv.x, acc[b][g]);
-            acc[b][g] = fmaf(w[g][4 * i + 1], hv.y, acc[b][g]);
-            acc[b][g] = fmaf(w[g][4 * i + 2], hv.z, acc[b][g]);
-            acc[b][g] = fmaf(w[g][4 * i + 3], hv.w, acc[b][g]);
+            acc2[b][g] = __ffma2_rn(w[g][2 * i + 0], h01, acc2[b][g]);
+            acc2[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, acc2[b][g]);
           }
         }
       }
+      float acc[BT][3];
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[b][g] = acc2[b][g].x + acc2[b][g].y;
       // ---- combine the G partial sums: own[o][g] = complete sum for sequence b = o*G + ql ----
       float own[NOWN][3];
       if constexpr (BT < G) {
@@ -209,15 +215,14 @@ int dispatch_bt(cudaStream_t st, const FwdParams& p, int bt) {
 
 }  // namespace
 
-// Sequences per CTA.  A CTA's cost per step grows far slower than BT (the weight registers are reused for every
-// sequence), so prefer BT = 2 as soon as that still gives every SM a CTA, and BT = 4 once even that oversubscribes
-// the resident-CTA capacity.
+// Sequences per CTA.  The recurrent kernels are bound by the per-step dependency chain (about 550 clk even with
+// no mat-vec work, measured with tools/probe_gru.py), so the fastest layout keeps every sequence in its own CTA
+// as long as all CTAs are co-resident; beyond that, two (then four) sequences share a CTA's weight registers.
 int tg_pick_bt(int B, int HP, int bt_override) {
   if (bt_override == 1 || bt_override == 2 || bt_override == 4) return bt_override;
-  const int sms = tg_num_sms();
-  const int occ = (HP <= 64) ? 3 : 1;
-  if (B < sms) return 1;                 // fewer sequences than SMs: one per CTA, spread as wide as possible
-  if (B <= 2 * sms * occ) return 2;
+  const int cap = tg_num_sms() * ((HP <= 64) ? 2 : 1);   // CTAs that run concurrently
+  if (B <= cap) return 1;
+  if (B <= 2 * cap) return 2;
   return 4;
 }
 

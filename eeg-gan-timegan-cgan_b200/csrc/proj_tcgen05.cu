@@ -207,11 +207,16 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_wait_bounded(&full[s], ph);
           float4* hi = reinterpret_cast<float4*>(a_base + (size_t)s * stage_bytes);
           float4* lo = reinterpret_cast<float4*>(a_base + (size_t)s * stage_bytes + a_bytes);
-          for (int i = t; i < a_bytes / 16; i += 128) {
-            float4 a = hi[i], h, l;
-            tf32_split(a.x, h.x, l.x); tf32_split(a.y, h.y, l.y); tf32_split(a.z, h.z, l.z); tf32_split(a.w, h.w, l.w);
-            hi[i] = h;
-            lo[i] = l;
+          // A_BLK_BYTES / 16 / 128 = 8 units per thread: all loads first, then split + stores
+          float4 a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = hi[t + j * 128];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 h, l;
+            tf32_split(a[j].x, h.x, l.x); tf32_split(a[j].y, h.y, l.y); tf32_split(a[j].z, h.z, l.z); tf32_split(a[j].w, h.w, l.w);
+            hi[t + j * 128] = h;
+            lo[t + j * 128] = l;
           }
           fence_async_smem();
           mbar_arrive(&split[s]);
