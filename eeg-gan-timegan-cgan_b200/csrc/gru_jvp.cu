@@ -8,7 +8,9 @@
 //   * gru_jvp_bwd : reverse of (primal + tangent) forward: two adjoint carries (for h and hdot), two
 //                   W_hh^T mat-vecs per step sharing the same register-resident weights.
 // Formulas are those of oracle/gru_math.py (gru_layer_jvp / gru_layer_jvp_bwd), which the CPU tests pin
-// against torch autograd.  Kernel structure is the same as gru_fwd.cu / gru_bwd.cu.
+// against torch autograd.  Kernel structure is the same as gru_fwd.cu / gru_bwd.cu: lane groups of G lanes per
+// hidden unit, packed FFMA2 mat-vecs, shuffle reduce-scatter to the lane that owns (unit, sequence), carried
+// states in that lane's registers, one __syncthreads per step.
 #include "chunk_pipe.cuh"
 #include "kernels.h"
 
@@ -27,9 +29,60 @@ struct JfParams {
   int bulk;
 };
 
+constexpr int JV_PAD = 16;   // smem state rows are HP+16 floats apart (bank spread between a lane pair's sequences)
+
+template <int HP, int G>
+constexpr int jvp_min_blocks() { return (HP * G <= 128) ? 2 : 1; }
+
+// lane-group combine shared by both kernels: own = complete sum for the sequence this lane owns
+// (b = ql when BT < G, else b = o*G + ql); NV values per sequence.
+template <int G, int BT, int NV>
+__device__ __forceinline__ void jvp_reduce_scatter(float (&acc)[BT][NV], float (&own)[(BT >= G) ? BT / G : 1][NV], int ql) {
+  constexpr int NOWN = (BT >= G) ? BT / G : 1;
+  if constexpr (BT < G) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      float mine = 0.f;
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float t = group_sum<G>(acc[b][v]);
+        mine = (ql == b) ? t : mine;
+      }
+      own[0][v] = mine;
+    }
+  } else if constexpr (G == 2) {
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float send = ql ? acc[2 * o][v] : acc[2 * o + 1][v];
+        const float keep = ql ? acc[2 * o + 1][v] : acc[2 * o][v];
+        own[o][v] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+  } else {
+    const int hi = ql & 2, lo = ql & 1;
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o)
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const float s0 = hi ? acc[4 * o + 0][v] : acc[4 * o + 2][v];
+        const float k0 = hi ? acc[4 * o + 2][v] : acc[4 * o + 0][v];
+        const float s1 = hi ? acc[4 * o + 1][v] : acc[4 * o + 3][v];
+        const float k1 = hi ? acc[4 * o + 3][v] : acc[4 * o + 1][v];
+        const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+        const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float send = lo ? a0 : a1;
+        const float keep = lo ? a1 : a0;
+        own[o][v] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+  }
+}
+
 template <int HP, int G, int BT, int TC, int NST>
-__global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_fwd_kernel(JfParams p) {
+__global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_fwd_kernel(JfParams p) {
   constexpr int KS = HP / G;
+  constexpr int NOWN = (BT >= G) ? BT / G : 1;
+  constexpr int HR = HP + JV_PAD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int j = tid / G, ql = tid % G;
@@ -37,9 +90,9 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_fwd_ke
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
-  float* hs = reinterpret_cast<float*>(smem_raw);  // [2][BT][HP]  tangent state
-  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * BT * HP);
-  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128);
+  float* hs = reinterpret_cast<float*>(smem_raw);  // [2][BT][HR]  tangent state
+  uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * BT * HR);
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128);
 
   ChunkPipe<6, BT, TC, NST> pipe;
   pipe.g[0] = pipe.gst[0] = p.gid;               pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | TG_STRM_STORE; pipe.shift[0] = 0;
@@ -53,7 +106,7 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_fwd_ke
   pipe.T = T; pipe.nb = nb; pipe.b0 = b0; pipe.NC = (T + TC - 1) / TC;
   pipe.reverse = false; pipe.bulk = p.bulk != 0;
 
-  float w[3][KS];
+  float2 w[3][KS / 2];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
@@ -61,9 +114,13 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_fwd_ke
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         int k = (i * G + ql) * 4 + c;
-        w[g][4 * i + c] = (j < H && k < H) ? p.whh[(size_t)(g * H + j) * H + k] : 0.f;
+        const float v = (j < H && k < H) ? p.whh[(size_t)(g * H + j) * H + k] : 0.f;
+        if (c & 1) w[g][2 * i + (c >> 1)].y = v; else w[g][2 * i + (c >> 1)].x = v;
       }
-  for (int i = tid; i < 2 * BT * HP; i += HP * G) hs[i] = 0.f;
+  for (int i = tid; i < 2 * BT * HR; i += HP * G) hs[i] = 0.f;
+  float hdprev[NOWN];
+#pragma unroll
+  for (int o = 0; o < NOWN; ++o) hdprev[o] = 0.f;
   pipe.start();
   __syncthreads();
 
@@ -74,44 +131,48 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_fwd_ke
     const int t0 = pipe.t0_of(c);
     const int tcn = pipe.tcn_of(c);
     for (int tl = 0; tl < tcn; ++tl) {
-      const float* hc = hs + cur * BT * HP;
-      float* hn = hs + (cur ^ 1) * BT * HP;
-      float acc[BT][3];
+      const float* hc = hs + cur * BT * HR;
+      float* hn = hs + (cur ^ 1) * BT * HR;
+      float2 acc2[BT][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc[b][0] = acc[b][1] = acc[b][2] = 0.f;
+      for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < KS / 4; ++i)
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-          const float4 hv = reinterpret_cast<const float4*>(hc + b * HP)[i * G + ql];
+          const float4 hv = reinterpret_cast<const float4*>(hc + b * HR)[i * G + ql];
+          const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
-            acc[b][g] = fmaf(w[g][4 * i + 0], hv.x, acc[b][g]);
-            acc[b][g] = fmaf(w[g][4 * i + 1], hv.y, acc[b][g]);
-            acc[b][g] = fmaf(w[g][4 * i + 2], hv.z, acc[b][g]);
-            acc[b][g] = fmaf(w[g][4 * i + 3], hv.w, acc[b][g]);
+            acc2[b][g] = __ffma2_rn(w[g][2 * i + 0], h01, acc2[b][g]);
+            acc2[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, acc2[b][g]);
           }
         }
+      float acc[BT][3], own[NOWN][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) {
+      for (int b = 0; b < BT; ++b)
 #pragma unroll
-        for (int g = 0; g < 3; ++g) acc[b][g] = group_sum<G>(acc[b][g]);
-        if (ql == (b % G) && j < H && b < nb) {
+        for (int g = 0; g < 3; ++g) acc[b][g] = acc2[b][g].x + acc2[b][g].y;
+      jvp_reduce_scatter<G, BT, 3>(acc, own, ql);
+#pragma unroll
+      for (int o = 0; o < NOWN; ++o) {
+        const int b = (BT < G) ? ql : o * G + ql;
+        if (j < H && b < nb) {
           float* gp = pipe.row(s, 0, b, tl);
           const float* sp = pipe.row(s, 1, b, tl);
           const float r = sp[j], z = sp[H + j], n = sp[2 * H + j];
           const float qv = pipe.row(s, 2, b, tl)[j];
           const float hp = (t0 + tl > 0) ? pipe.row(s, 3, b, tl)[j] : 0.f;
-          const float hdp = hc[b * HP + j];
-          const float a_r = gp[j] + acc[b][0];
-          const float a_z = gp[H + j] + acc[b][1];
-          const float qd = acc[b][2];
+          const float a_r = gp[j] + own[o][0];
+          const float a_z = gp[H + j] + own[o][1];
+          const float qd = own[o][2];
           const float rdot = r * (1.f - r) * a_r;
           const float zdot = z * (1.f - z) * a_z;
           const float a_n = gp[2 * H + j] + rdot * qv + r * qd;
           const float ndot = (1.f - n * n) * a_n;
-          const float hd = (1.f - z) * ndot + z * hdp + zdot * (hp - n);
-          hn[b * HP + j] = hd;
+          const float hd = (1.f - z) * ndot + z * hdprev[o] + zdot * (hp - n);
+          hdprev[o] = hd;
+          hn[b * HR + j] = hd;
           gp[j] = a_r; gp[H + j] = a_z; gp[2 * H + j] = a_n;
           pipe.row(s, 4, b, tl)[j] = qd;
           pipe.row(s, 5, b, tl)[j] = hd;
@@ -147,8 +208,10 @@ struct JbParams {
 };
 
 template <int HP, int G, int BT, int TC, int NST>
-__global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_kernel(JbParams p) {
+__global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_bwd_kernel(JbParams p) {
   constexpr int KS = HP / G;
+  constexpr int NOWN = (BT >= G) ? BT / G : 1;
+  constexpr int HR = HP + JV_PAD;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int k = tid / G, ql = tid % G;
@@ -156,9 +219,9 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
-  float* dgs = reinterpret_cast<float*>(smem_raw);  // [2][BT][6][HP] : primal dGH (3) then tangent dGH (3)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(dgs + 2 * BT * 6 * HP);
-  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * 6 * HP * 4 + NST * 8 + 127) / 128) * 128);
+  float* dgs = reinterpret_cast<float*>(smem_raw);  // [2][BT][6][HR] : primal dGH (3) then tangent dGH (3)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dgs + 2 * BT * 6 * HR);
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * 6 * HR * 4 + NST * 8 + 127) / 128) * 128);
 
   ChunkPipe<8, BT, TC, NST> pipe;
   const int ld = TG_STRM_LOAD, lst = TG_STRM_LOAD | TG_STRM_STORE;
@@ -175,7 +238,7 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
   pipe.T = T; pipe.nb = nb; pipe.b0 = b0; pipe.NC = (T + TC - 1) / TC;
   pipe.reverse = true; pipe.bulk = p.bulk != 0;
 
-  float wt[3][KS];
+  float2 wt[3][KS / 2];
 #pragma unroll
   for (int g = 0; g < 3; ++g)
 #pragma unroll
@@ -183,12 +246,13 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         int jj = (i * G + ql) * 4 + c;
-        wt[g][4 * i + c] = (k < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + k] : 0.f;
+        const float v = (k < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + k] : 0.f;
+        if (c & 1) wt[g][2 * i + (c >> 1)].y = v; else wt[g][2 * i + (c >> 1)].x = v;
       }
-  for (int i = tid; i < 2 * BT * 6 * HP; i += HP * G) dgs[i] = 0.f;
-  float ch[BT], chd[BT];
+  for (int i = tid; i < 2 * BT * 6 * HR; i += HP * G) dgs[i] = 0.f;
+  float ch[NOWN], chd[NOWN];
 #pragma unroll
-  for (int b = 0; b < BT; ++b) ch[b] = chd[b] = 0.f;
+  for (int o = 0; o < NOWN; ++o) ch[o] = chd[o] = 0.f;
   pipe.start();
   __syncthreads();
 
@@ -200,12 +264,13 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
     const int tcn = pipe.tcn_of(c);
     for (int tl = tcn - 1; tl >= 0; --tl) {
       const int t = t0 + tl;
-      float* dg = dgs + par * BT * 6 * HP;
-      float nh[BT], nhd[BT];
+      float* dg = dgs + par * BT * 6 * HR;
+      float nh[NOWN], nhd[NOWN];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) {
-        nh[b] = nhd[b] = 0.f;
-        if (ql == (b % G) && k < H && b < nb) {
+      for (int o = 0; o < NOWN; ++o) {
+        const int b = (BT < G) ? ql : o * G + ql;
+        nh[o] = nhd[o] = 0.f;
+        if (k < H && b < nb) {
           float* gp = pipe.row(s, 0, b, tl);
           float* qp = pipe.row(s, 1, b, tl);
           float* tp = pipe.row(s, 2, b, tl);
@@ -222,8 +287,8 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
             hb = pipe.row(s, 6, b, tl)[k];
             hdb = pipe.row(s, 7, b, tl)[k];
           }
-          hb += ch[b];
-          hdb += chd[b];
+          hb += ch[o];
+          hdb += chd[o];
           const float sr = rt * (1.f - rt), sz = zt * (1.f - zt), sn = 1.f - nt * nt;
           const float rdot = sr * art, zdot = sz * azt, ndot = sn * ant;
           // hdot_t = (1-z) ndot + z hdot_{t-1} + zdot (h_{t-1} - n)
@@ -231,12 +296,12 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
           float zb = hdb * (hdp - ndot);
           const float zdb = hdb * (hp - nt);
           float nb_ = -zdot * hdb;
-          nh[b] = zdot * hdb;
-          nhd[b] = zt * hdb;
+          nh[o] = zdot * hdb;
+          nhd[o] = zt * hdb;
           // h_t = n + z (h_{t-1} - n)
           nb_ += (1.f - zt) * hb;
           zb += hb * (hp - nt);
-          nh[b] += zt * hb;
+          nh[o] += zt * hb;
           // ndot = (1-n^2) a_n
           const float anb_d = sn * ndb;
           nb_ -= 2.f * nt * ant * ndb;
@@ -258,37 +323,42 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
           const float arb = sr * rb;
           gp[k] = arb; gp[H + k] = azb; gp[2 * H + k] = anb; qp[k] = qb;
           tp[k] = arb_d; tp[H + k] = azb_d; tp[2 * H + k] = anb_d; qdp[k] = qdb;
-          float* d0 = dg + (b * 6) * HP;
-          d0[0 * HP + k] = arb;   d0[1 * HP + k] = azb;   d0[2 * HP + k] = qb;
-          d0[3 * HP + k] = arb_d; d0[4 * HP + k] = azb_d; d0[5 * HP + k] = qdb;
+          float* d0 = dg + (b * 6) * HR;
+          d0[0 * HR + k] = arb;   d0[1 * HR + k] = azb;   d0[2 * HR + k] = qb;
+          d0[3 * HR + k] = arb_d; d0[4 * HR + k] = azb_d; d0[5 * HR + k] = qdb;
         }
       }
       if (tl == 0 && pipe.bulk) fence_async_smem();
       __syncthreads();
-      float acc[BT][2];
+      float2 a2[BT][2][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc[b][0] = acc[b][1] = 0.f;
+      for (int b = 0; b < BT; ++b)
 #pragma unroll
-      for (int g = 0; g < 3; ++g)
+        for (int v = 0; v < 2; ++v) a2[b][v][0] = a2[b][v][1] = a2[b][v][2] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < KS / 4; ++i)
+      for (int i = 0; i < KS / 4; ++i)
+#pragma unroll
+        for (int g = 0; g < 3; ++g)
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
-            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 6 + g) * HP)[i * G + ql];
-            const float4 ev = reinterpret_cast<const float4*>(dg + (b * 6 + 3 + g) * HP)[i * G + ql];
-            acc[b][0] = fmaf(wt[g][4 * i + 0], dv.x, acc[b][0]);
-            acc[b][1] = fmaf(wt[g][4 * i + 0], ev.x, acc[b][1]);
-            acc[b][0] = fmaf(wt[g][4 * i + 1], dv.y, acc[b][0]);
-            acc[b][1] = fmaf(wt[g][4 * i + 1], ev.y, acc[b][1]);
-            acc[b][0] = fmaf(wt[g][4 * i + 2], dv.z, acc[b][0]);
-            acc[b][1] = fmaf(wt[g][4 * i + 2], ev.z, acc[b][1]);
-            acc[b][0] = fmaf(wt[g][4 * i + 3], dv.w, acc[b][0]);
-            acc[b][1] = fmaf(wt[g][4 * i + 3], ev.w, acc[b][1]);
+            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 6 + g) * HR)[i * G + ql];
+            const float4 ev = reinterpret_cast<const float4*>(dg + (b * 6 + 3 + g) * HR)[i * G + ql];
+            a2[b][0][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(dv.x, dv.y), a2[b][0][g]);
+            a2[b][1][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(ev.x, ev.y), a2[b][1][g]);
+            a2[b][0][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(dv.z, dv.w), a2[b][0][g]);
+            a2[b][1][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(ev.z, ev.w), a2[b][1][g]);
           }
+      float acc[BT][2], own[NOWN][2];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) {
-        ch[b] = nh[b] + group_sum<G>(acc[b][0]);
-        chd[b] = nhd[b] + group_sum<G>(acc[b][1]);
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+          acc[b][v] = (a2[b][v][0].x + a2[b][v][0].y) + (a2[b][v][1].x + a2[b][v][1].y) + (a2[b][v][2].x + a2[b][v][2].y);
+      jvp_reduce_scatter<G, BT, 2>(acc, own, ql);
+#pragma unroll
+      for (int o = 0; o < NOWN; ++o) {
+        ch[o] = nh[o] + own[o][0];
+        chd[o] = nhd[o] + own[o][1];
       }
       par ^= 1;
     }
@@ -300,7 +370,8 @@ __global__ void __launch_bounds__(HP* G, (HP * G <= 256) ? 2 : 1) gru_jvp_bwd_ke
 template <int HP, int G, int BT, int TC, int NST>
 int launch_jf(cudaStream_t st, const JfParams& p) {
   const int widths[6] = {3 * p.H, 3 * p.H, p.H, p.H, p.H, p.H};
-  size_t smem = ((2 * BT * HP * 4 + NST * 8 + 127) / 128) * 128 +
+  constexpr int HR = HP + JV_PAD;
+  size_t smem = ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<6, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_jvp_fwd_kernel<HP, G, BT, TC, NST>;
   TG_OPT_IN_SMEM(kern, "gru_jvp_fwd");
@@ -312,7 +383,8 @@ int launch_jf(cudaStream_t st, const JfParams& p) {
 template <int HP, int G, int BT, int TC, int NST>
 int launch_jb(cudaStream_t st, const JbParams& p) {
   const int widths[8] = {3 * p.H, p.H, 3 * p.H, p.H, p.H, p.H, p.H, p.H};
-  size_t smem = ((2 * BT * 6 * HP * 4 + NST * 8 + 127) / 128) * 128 +
+  constexpr int HR = HP + JV_PAD;
+  size_t smem = ((2 * BT * 6 * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<8, BT, TC, NST>::stage_floats_for(widths) * 4;
   auto kern = gru_jvp_bwd_kernel<HP, G, BT, TC, NST>;
   TG_OPT_IN_SMEM(kern, "gru_jvp_bwd");
@@ -347,8 +419,8 @@ int tg_gru_jvp_fwd_impl(cudaStream_t st, float* gid, const float* rzn, const flo
   p.bulk = (H % 4 == 0) && tg_aligned16(gid) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(y) &&
            tg_aligned16(ydot) && tg_aligned16(qdot) && !(flags & TG_GRU_NO_BULK);
   const int bto = (flags >> 8) & 0xff;
-  if (H <= 32) return dispatch_jf<32, 4>(st, p, tg_pick_bt(B, 32, bto));
-  if (H <= 64) return dispatch_jf<64, 4>(st, p, tg_pick_bt(B, 64, bto));
+  if (H <= 32) return dispatch_jf<32, 2>(st, p, tg_pick_bt(B, 32, bto));
+  if (H <= 64) return dispatch_jf<64, 2>(st, p, tg_pick_bt(B, 64, bto));
   return dispatch_jf<128, 4>(st, p, tg_pick_bt(B, 128, bto));
 }
 
@@ -366,7 +438,7 @@ int tg_gru_jvp_bwd_impl(cudaStream_t st, const float* hbar, const float* hdbar, 
            tg_aligned16(qdb) && (p.last_only || (tg_aligned16(hbar) && tg_aligned16(hdbar))) &&
            !(flags & TG_GRU_NO_BULK);
   const int bto = (flags >> 8) & 0xff;
-  if (H <= 32) return dispatch_jb<32, 4>(st, p, tg_pick_bt(B, 32, bto));
-  if (H <= 64) return dispatch_jb<64, 4>(st, p, tg_pick_bt(B, 64, bto));
+  if (H <= 32) return dispatch_jb<32, 2>(st, p, tg_pick_bt(B, 32, bto));
+  if (H <= 64) return dispatch_jb<64, 2>(st, p, tg_pick_bt(B, 64, bto));
   return dispatch_jb<128, 4>(st, p, tg_pick_bt(B, 128, bto));
 }
