@@ -200,8 +200,7 @@ def run_ours(a):
     import timegan_b200 as tg
     from timegan_b200 import _lib, ops, dist as tdist, train_timegan as tt
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout (one JSON line only)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/null")   # keep NCCL's version banner off stdout (one JSON line)
         tdist.init(backend="nccl", device=dev)
     ops.set_proj_mode(a.proj)
     tt.set_concurrency(not a.serial)
@@ -209,7 +208,9 @@ def run_ours(a):
     torch.manual_seed(42)
     model = tg.TimeGAN(X_DIM, a.hidden, a.hidden, a.layers, 0.0).to(dev)
     P = tt._params
-    use_graph = not a.no_graph
+    # CUDA-graph replay is used on one GPU; under data parallelism the step is issued eagerly (capturing the NCCL
+    # all-reduces together with the side-stream forks hung in round 1 -- to be revisited)
+    use_graph = (not a.no_graph) and world == 1
     optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"], capturable=use_graph)
     optG = tg.FusedAdam(P(model.generator, model.supervisor, model.embedder, model.recovery), lr=HP["lr_g"],
                         betas=HP["betas"], capturable=use_graph)

@@ -17,7 +17,8 @@
 
 namespace {
 
-constexpr int WL_THREADS = 320;
+constexpr int WL_THREADS = 448;   // TMA, MMA, 4 epilogue warps, 8 fix-up warps
+constexpr int WL_FIX = 256;
 constexpr int WL_TAIL = 1024;
 constexpr int WL_MAXCH = 16;   // chunks of the A operand (dGI + dq)
 
@@ -57,7 +58,7 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
   const int steps = row_begin < row_end ? (int)((row_end - row_begin + R - 1) / R) : 0;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], 128); }
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&ready[s], WL_FIX); }
     mbar_init(acc_full, 1);
     mbar_fence_init();
   }
@@ -160,13 +161,17 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       }
     }
   } else {
-    // ===================== fix-up / split / column-sum warps (6..9) =====================
+    // ===================== fix-up / split / column-sum warps (6..13) =====================
+    // two groups of 128 threads take the even / odd chunks of every stage; inside a group thread (u, rsub)
+    // owns the 16-byte unit u of the rows r == rsub (mod 16)
     const int t = threadIdx.x - 192;
-    const int u = t & 7, rsub = t >> 3;
+    const int grp = t >> 7, tt = t & 127;
+    const int u = tt & 7, rsub = tt >> 3;
     const int cu = ((((u >> 1) ^ (rsub & 3)) << 1) | (u & 1));
-    float4 colsum[WL_MAXCH];
+    float4 colsum[WL_MAXCH / 2];
 #pragma unroll
-    for (int c = 0; c < WL_MAXCH; ++c) colsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < WL_MAXCH / 2; ++c) colsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int NCHK = GCH + ACH;
     for (int it = 0; it < steps; ++it) {
       const int s = it % NS;
       mbar_wait_bounded(&full[s], (uint32_t)((it / NS) & 1));
@@ -177,55 +182,47 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       unsigned char* base = smem + (size_t)s * stage_bytes;
       unsigned char* lo = lo_base + (size_t)(it & 1) * stage_bytes;
       const long long r0 = row_begin + (long long)it * R;
-      // (1) y rows that would pair dG[m] with the previous sequence's last state
       for (int r = rsub; r < R; r += 16) {
-        if ((r0 + r) % p.T == 0) {
-          for (int c = 0; c < p.a2ch; ++c)
-            reinterpret_cast<float4*>(base + (GCH + p.a1ch + c) * chunk_bytes + r * 128)[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      // (2) dGI / dq: column sums (+ split)
+        const bool boundary = ((r0 + r) % p.T) == 0;
+        const size_t off = (size_t)r * 128 + (size_t)u * 16;
 #pragma unroll
-      for (int c = 0; c < WL_MAXCH; ++c) {
-        if (c < GCH) {
-          for (int r = rsub; r < R; r += 16) {
-            float4* ptr = reinterpret_cast<float4*>(base + c * chunk_bytes + r * 128) + u;
-            const float4 a = *ptr;
-            colsum[c].x += a.x; colsum[c].y += a.y; colsum[c].z += a.z; colsum[c].w += a.w;
+        for (int ci = 0; ci < (WL_MAXCH + 8) / 2; ++ci) {
+          const int c = 2 * ci + grp;
+          if (c < NCHK) {
+            float4* ptr = reinterpret_cast<float4*>(base + (size_t)c * chunk_bytes + off);
+            float4 a = *ptr;
+            if (ci < WL_MAXCH / 2 && c < GCH) {
+              colsum[ci < WL_MAXCH / 2 ? ci : 0].x += a.x; colsum[ci < WL_MAXCH / 2 ? ci : 0].y += a.y;
+              colsum[ci < WL_MAXCH / 2 ? ci : 0].z += a.z; colsum[ci < WL_MAXCH / 2 ? ci : 0].w += a.w;
+            }
+            const bool kill = boundary && c >= GCH + p.a1ch;     // y row that belongs to the previous sequence
+            if (kill) a = make_float4(0.f, 0.f, 0.f, 0.f);
             if (PASSES == 3) {
               float4 h, l;
               tf32_split(a.x, h.x, l.x); tf32_split(a.y, h.y, l.y); tf32_split(a.z, h.z, l.z); tf32_split(a.w, h.w, l.w);
               *ptr = h;
-              *(reinterpret_cast<float4*>(lo + c * chunk_bytes + r * 128) + u) = l;
+              *reinterpret_cast<float4*>(lo + (size_t)c * chunk_bytes + off) = l;
+            } else if (kill) {
+              *ptr = a;
             }
           }
         }
-      }
-      // (3) x / y: split
-      if (PASSES == 3) {
-        for (int c = GCH; c < GCH + ACH; ++c)
-          for (int r = rsub; r < R; r += 16) {
-            float4* ptr = reinterpret_cast<float4*>(base + c * chunk_bytes + r * 128) + u;
-            const float4 a = *ptr;
-            float4 h, l;
-            tf32_split(a.x, h.x, l.x); tf32_split(a.y, h.y, l.y); tf32_split(a.z, h.z, l.z); tf32_split(a.w, h.w, l.w);
-            *ptr = h;
-            *(reinterpret_cast<float4*>(lo + c * chunk_bytes + r * 128) + u) = l;
-          }
       }
       fence_async_smem();
       mbar_arrive(&ready[s]);
     }
     // per-CTA column-sum partial (bias gradients)
     mbar_wait_bounded(acc_full, 0);
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-    for (int c = 0; c < WL_MAXCH; ++c)
-      if (c < GCH) *reinterpret_cast<float4*>(db_red + (size_t)rsub * (GCH * 32) + c * 32 + cu * 4) = colsum[c];
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    for (int ci = 0; ci < WL_MAXCH / 2; ++ci) {
+      const int c = 2 * ci + grp;
+      if (c < GCH) *reinterpret_cast<float4*>(db_red + (size_t)rsub * (GCH * 32) + c * 32 + cu * 4) = colsum[ci];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     float* cs = p.ws + (size_t)blockIdx.x * ((size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H + GCH * 32) +
                 (size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H;
-    for (int n = t; n < GCH * 32; n += 128) {
+    for (int n = t; n < GCH * 32; n += WL_FIX) {
       float sum = 0.f;
 #pragma unroll
       for (int r = 0; r < 16; ++r) sum += db_red[(size_t)r * (GCH * 32) + n];
