@@ -185,27 +185,32 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       for (int r = rsub; r < R; r += 16) {
         const bool boundary = ((r0 + r) % p.T) == 0;
         const size_t off = (size_t)r * 128 + (size_t)u * 16;
-#pragma unroll
-        for (int ci = 0; ci < (WL_MAXCH + 8) / 2; ++ci) {
-          const int c = 2 * ci + grp;
-          if (c < NCHK) {
-            float4* ptr = reinterpret_cast<float4*>(base + (size_t)c * chunk_bytes + off);
-            float4 a = *ptr;
-            if (ci < WL_MAXCH / 2 && c < GCH) {
-              colsum[ci < WL_MAXCH / 2 ? ci : 0].x += a.x; colsum[ci < WL_MAXCH / 2 ? ci : 0].y += a.y;
-              colsum[ci < WL_MAXCH / 2 ? ci : 0].z += a.z; colsum[ci < WL_MAXCH / 2 ? ci : 0].w += a.w;
-            }
-            const bool kill = boundary && c >= GCH + p.a1ch;     // y row that belongs to the previous sequence
-            if (kill) a = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (PASSES == 3) {
-              float4 h, l;
-              tf32_split(a.x, h.x, l.x); tf32_split(a.y, h.y, l.y); tf32_split(a.z, h.z, l.z); tf32_split(a.w, h.w, l.w);
-              *ptr = h;
-              *reinterpret_cast<float4*>(lo + (size_t)c * chunk_bytes + off) = l;
-            } else if (kill) {
-              *ptr = a;
-            }
+        // three chunks per batch: the loads are issued together (the compiler cannot reorder them across the
+        // in-place stores by itself), then column sums / h_{-1} zeroing / TF32 split, then the stores
+        auto finish = [&](int c, int ci, float4 a) {
+          if (c < GCH) { colsum[ci & 7].x += a.x; colsum[ci & 7].y += a.y; colsum[ci & 7].z += a.z; colsum[ci & 7].w += a.w; }
+          const bool kill = boundary && c >= GCH + p.a1ch;     // y row that belongs to the previous sequence
+          if (kill) a = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* ptr = reinterpret_cast<float4*>(base + (size_t)c * chunk_bytes + off);
+          if (PASSES == 3) {
+            float4 h, l;
+            tf32_split(a.x, h.x, l.x); tf32_split(a.y, h.y, l.y); tf32_split(a.z, h.z, l.z); tf32_split(a.w, h.w, l.w);
+            *ptr = h;
+            *reinterpret_cast<float4*>(lo + (size_t)c * chunk_bytes + off) = l;
+          } else if (kill) {
+            *ptr = a;
           }
+        };
+#pragma unroll
+        for (int cb = 0; cb < (WL_MAXCH + 8) / 2; cb += 3) {
+          const int c0 = 2 * cb + grp, c1 = c0 + 2, c2 = c0 + 4;
+          float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
+          if (c0 < NCHK) a0 = *reinterpret_cast<const float4*>(base + (size_t)c0 * chunk_bytes + off);
+          if (c1 < NCHK) a1 = *reinterpret_cast<const float4*>(base + (size_t)c1 * chunk_bytes + off);
+          if (c2 < NCHK) a2 = *reinterpret_cast<const float4*>(base + (size_t)c2 * chunk_bytes + off);
+          if (c0 < NCHK) finish(c0, cb, a0);
+          if (c1 < NCHK) finish(c1, cb + 1, a1);
+          if (c2 < NCHK) finish(c2, cb + 2, a2);
         }
       }
       fence_async_smem();
