@@ -59,6 +59,10 @@ struct ChunkPipe {
     int t0 = t0_of(c);
     return min(TC, T - t0);
   }
+  // 32-bit shared-window address of a row (for the ld.shared / st.shared helpers of common.cuh)
+  __device__ __forceinline__ uint32_t row_addr(int s, int k, int b, int tl) const {
+    return smem_u32(stages) + 4u * (uint32_t)(s * stage_floats + off[k] + b * bstride[k] + tl * w[k]);
+  }
   __device__ __forceinline__ float* row(int s, int k, int b, int tl) const {
     return stages + (size_t)s * stage_floats + off[k] + b * bstride[k] + tl * w[k];
   }

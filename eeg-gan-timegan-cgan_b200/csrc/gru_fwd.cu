@@ -87,14 +87,42 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
   pipe.start();
   __syncthreads();
 
+  // per-thread constants of the hot loop: which sequences this lane finishes, shared-window addresses
+  const uint32_t hs_addr = smem_u32(hs);
+  bool act[NOWN];
+  int ob[NOWN];
+#pragma unroll
+  for (int o = 0; o < NOWN; ++o) {
+    ob[o] = (BT < G) ? ql : o * G + ql;
+    act[o] = (j < H) && (ob[o] < nb);
+  }
+  const uint32_t gi_step = 12u * (uint32_t)H, h_step = 4u * (uint32_t)H;
+  const uint32_t lane_k = 16u * (uint32_t)ql;          // this lane's first float4 of h
+  const bool save = p.save != 0;
+
   int cur = 0;
   for (int c = 0; c < pipe.NC; ++c) {
     pipe.acquire(c);
     const int s = c % NST;
     const int tcn = pipe.tcn_of(c);
+    uint32_t a_gi[NOWN], a_q[NOWN], a_y[NOWN];
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const int b = act[o] ? ob[o] : 0;
+      a_gi[o] = pipe.row_addr(s, 0, b, 0) + 4u * (uint32_t)j;
+      a_q[o] = pipe.row_addr(s, 1, b, 0) + 4u * (uint32_t)j;
+      a_y[o] = pipe.row_addr(s, 2, b, 0) + 4u * (uint32_t)j;
+    }
     for (int tl = 0; tl < tcn; ++tl) {
-      const float* hc = hs + cur * BT * HR;
-      float* hn = hs + (cur ^ 1) * BT * HR;
+      const uint32_t hc = hs_addr + (uint32_t)(cur * BT * HR) * 4u;
+      const uint32_t hn = hs_addr + (uint32_t)((cur ^ 1) * BT * HR) * 4u;
+      // the input-projection values are fetched first so that their latency hides behind the mat-vec
+      float gr[NOWN], gz[NOWN], gn[NOWN];
+#pragma unroll
+      for (int o = 0; o < NOWN; ++o) {
+        gr[o] = gz[o] = gn[o] = 0.f;
+        if (act[o]) { gr[o] = lds_f32(a_gi[o]); gz[o] = lds_f32(a_gi[o] + h_step); gn[o] = lds_f32(a_gi[o] + 2u * h_step); }
+      }
       float2 acc2[BT][3];
 #pragma unroll
       for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
@@ -102,7 +130,7 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
       for (int i = 0; i < KS / 4; ++i) {
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
-          const float4 hv = reinterpret_cast<const float4*>(hc + b * HR)[i * G + ql];
+          const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u + lane_k);
           const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
@@ -145,14 +173,12 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
         for (int o = 0; o < NOWN; ++o)
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
-            // round 1 (xor 2): keep the pair {4o + (hi), 4o + (hi) + 1}
             const float s0 = hi ? acc[4 * o + 0][g] : acc[4 * o + 2][g];
             const float k0 = hi ? acc[4 * o + 2][g] : acc[4 * o + 0][g];
             const float s1 = hi ? acc[4 * o + 1][g] : acc[4 * o + 3][g];
             const float k1 = hi ? acc[4 * o + 3][g] : acc[4 * o + 1][g];
             const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
             const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-            // round 2 (xor 1)
             const float send = lo ? a0 : a1;
             const float keep = lo ? a1 : a0;
             own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
@@ -161,22 +187,21 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
       // ---- gates + state update for the sequences this lane owns ----
 #pragma unroll
       for (int o = 0; o < NOWN; ++o) {
-        const int b = (BT < G) ? ql : o * G + ql;
-        if (j < H && b < nb) {
-          float* gp = pipe.row(s, 0, b, tl);
-          const float r = sigmoid_fast(gp[j] + own[o][0] + bh[0]);
-          const float z = sigmoid_fast(gp[H + j] + own[o][1] + bh[1]);
+        if (act[o]) {
+          const float r = sigmoid_mufu(gr[o] + own[o][0] + bh[0]);
+          const float z = sigmoid_mufu(gz[o] + own[o][1] + bh[1]);
           const float qv = own[o][2] + bh[2];
-          const float n = tanh_fast(fmaf(r, qv, gp[2 * H + j]));
+          const float n = tanh_mufu(fmaf(r, qv, gn[o]));
           const float h = fmaf(z, hprev[o] - n, n);
           hprev[o] = h;
-          hn[b * HR + j] = h;
-          pipe.row(s, 2, b, tl)[j] = h;
-          if (p.save) {
-            gp[j] = r; gp[H + j] = z; gp[2 * H + j] = n;
-            pipe.row(s, 1, b, tl)[j] = qv;
+          sts_f32(hn + (uint32_t)(ob[o] * HR + j) * 4u, h);
+          sts_f32(a_y[o], h);
+          if (save) {
+            sts_f32(a_gi[o], r); sts_f32(a_gi[o] + h_step, z); sts_f32(a_gi[o] + 2u * h_step, n);
+            sts_f32(a_q[o], qv);
           }
         }
+        a_gi[o] += gi_step; a_q[o] += h_step; a_y[o] += h_step;
       }
       if (tl == tcn - 1 && pipe.bulk) fence_async_smem();
       __syncthreads();
