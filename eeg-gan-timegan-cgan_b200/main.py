@@ -38,7 +38,8 @@ def kwargs_from_config(cfg: Dict[str, Any]) -> Dict[str, Any]:
         seed=int(g("seed", 42)), r1_gamma=float(g("r1_gamma", 1.0)), d_min_acc=float(g("d_min_acc", 0.45)),
         d_max_acc=float(g("d_max_acc", 0.60)), gamma_cov=float(g("gamma_cov", 0.05)),
         gamma_acf=float(g("gamma_acf", 0.05)), acf_max_lag=int(g("acf_max_lag", 64)))
-    for k, cast in (("z_dim", int), ("hidden_dim", int), ("proj_dtype", str), ("noise", str), ("log_every", int)):
+    for k, cast in (("z_dim", int), ("hidden_dim", int), ("proj_dtype", str), ("noise", str), ("log_every", int),
+                    ("graph", bool)):
         if g(k) is not None:
             kw[k] = cast(g(k))
     return kw

@@ -524,11 +524,14 @@ def train_single_npz(npz_path: Path, out_dir: Path,
                      hidden_dim: Optional[int] = None,
                      noise: Optional[str] = None,
                      proj_dtype: str = "fp32",
-                     log_every: int = 1):
+                     log_every: int = 1,
+                     graph: bool = False):
     """Same schedule, logs and artefacts as the reference.  Extras (keyword-only): `z_dim`/`hidden_dim`
     override adaptive_dims; `noise="host"` replays the reference's CPU random stream (parity runs), default is
     on-device Philox; `proj_dtype` "fp32" | "bf16" (tensor-core input projections); `log_every` k > 1 keeps
-    the per-step scalars on the device and flushes CSV rows / best-checkpoint decisions every k steps."""
+    the per-step scalars on the device and flushes CSV rows / best-checkpoint decisions every k steps;
+    `graph=True` replays the joint step from a CUDA graph (GraphedJointStep; full-size batches only -- the ragged
+    last batch of an epoch runs eagerly -- on-device noise, one GPU)."""
     npz_path, out_dir = Path(npz_path), Path(out_dir)
     set_seeds(seed)
     device = device or device_autoselect()
@@ -568,8 +571,10 @@ def train_single_npz(npz_path: Path, out_dir: Path,
     optS = FusedAdam(model.supervisor.parameters(), lr=lr_g, betas=betas)
     phase_supervisor(model, loader, device, optS, grad_clip, sup_epochs, LOG)
 
-    optD = FusedAdam(model.discriminator.parameters(), lr=lr_d, betas=betas)
-    optG = FusedAdam(_params(model.generator, model.supervisor, model.embedder, model.recovery), lr=lr_g, betas=betas)
+    use_graph = bool(graph) and nz is None and not _dist.is_enabled()
+    optD = FusedAdam(model.discriminator.parameters(), lr=lr_d, betas=betas, capturable=use_graph)
+    optG = FusedAdam(_params(model.generator, model.supervisor, model.embedder, model.recovery), lr=lr_g, betas=betas,
+                     capturable=use_graph)
     milestones = [gan_steps // 2, int(gan_steps * 0.75)]
     schedulerG = optim.lr_scheduler.MultiStepLR(optG, milestones=milestones, gamma=0.5)
     schedulerD = optim.lr_scheduler.MultiStepLR(optD, milestones=milestones, gamma=0.5)
@@ -583,6 +588,12 @@ def train_single_npz(npz_path: Path, out_dir: Path,
     target = 0.5 * (d_min_acc + d_max_acc)
     band = max(0.0, d_max_acc - d_min_acc)
     pending = []   # (step, device scalars) awaiting a flush
+    graphed = None
+    if use_graph:
+        graphed = GraphedJointStep(model, optD, optG, device, label_smooth=label_smooth, clip=grad_clip,
+                                   r1_gamma=r1_gamma, target_acc=target, band=band, alpha_sup=alpha_sup,
+                                   beta_rec=beta_rec, gamma_cov=gamma_cov, gamma_acf=gamma_acf, acf_max_lag=acf_max_lag,
+                                   schedulerD=schedulerD, schedulerG=schedulerG)
 
     def flush():
         nonlocal best_ckpt_loss
@@ -614,11 +625,15 @@ def train_single_npz(npz_path: Path, out_dir: Path,
             (x_batch,) = next(loader_iter)
         x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
 
-        d_loss, d_acc = disc_step(model, x, device, optD, label_smooth, inst_noise, grad_clip, schedulerD, r1_gamma,
-                                  target_acc=target, band=band, noise=nz, sync=False)
-        g_vals = gen_step(model, x, device, optG, alpha_sup, beta_rec, inst_noise, grad_clip, schedulerG, gamma_cov,
-                          gamma_acf, acf_max_lag, noise=nz, sync=False)
-        pending.append((step, (d_loss, d_acc) + tuple(g_vals)))
+        if graphed is not None and x.shape[0] == batch_size and inst_noise > 0:
+            vals = graphed(x, inst_noise).clone()           # the graph's output buffer is reused by the next replay
+            pending.append((step, tuple(vals.unbind(0))))
+        else:
+            d_loss, d_acc = disc_step(model, x, device, optD, label_smooth, inst_noise, grad_clip, schedulerD, r1_gamma,
+                                      target_acc=target, band=band, noise=nz, sync=False)
+            g_vals = gen_step(model, x, device, optG, alpha_sup, beta_rec, inst_noise, grad_clip, schedulerG, gamma_cov,
+                              gamma_acf, acf_max_lag, noise=nz, sync=False)
+            pending.append((step, (d_loss, d_acc) + tuple(g_vals)))
         if len(pending) >= max(1, log_every) or step == gan_steps:
             flush()
 
@@ -673,6 +688,7 @@ def build_argparser():
     ap.add_argument("--proj_dtype", type=str, default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--noise", type=str, default=None, choices=[None, "host"])
     ap.add_argument("--log_every", type=int, default=1)
+    ap.add_argument("--graph", action="store_true", help="replay the joint step from a CUDA graph")
     return ap
 
 
@@ -696,7 +712,7 @@ def main(argv=None):
             layers=args.layers, dropout=args.dropout, seed=args.seed, r1_gamma=args.r1_gamma,
             d_min_acc=args.d_min_acc, d_max_acc=args.d_max_acc, gamma_cov=args.gamma_cov, gamma_acf=args.gamma_acf,
             acf_max_lag=args.acf_max_lag, device=device, z_dim=args.z_dim, hidden_dim=args.hidden_dim,
-            proj_dtype=args.proj_dtype, noise=args.noise, log_every=args.log_every)
+            proj_dtype=args.proj_dtype, noise=args.noise, log_every=args.log_every, graph=args.graph)
 
 
 if __name__ == "__main__":
