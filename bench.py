@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial", action="store_true", help="disable side-stream concurrency inside the step")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dp-graph", action="store_true", help="experimental: capture the NCCL all-reduces too (N > 1)")
     ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
     return ap.parse_args()
 
@@ -210,7 +211,7 @@ def run_ours(a):
     P = tt._params
     # CUDA-graph replay is used on one GPU; under data parallelism the step is issued eagerly (capturing the NCCL
     # all-reduces together with the side-stream forks hung in round 1 -- to be revisited)
-    use_graph = (not a.no_graph) and world == 1
+    use_graph = (not a.no_graph) and (world == 1 or a.dp_graph)
     optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"], capturable=use_graph)
     optG = tg.FusedAdam(P(model.generator, model.supervisor, model.embedder, model.recovery), lr=HP["lr_g"],
                         betas=HP["betas"], capturable=use_graph)

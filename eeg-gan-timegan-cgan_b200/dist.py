@@ -137,6 +137,15 @@ class GradBuckets:
             td.all_reduce(flat, op=td.ReduceOp.SUM, group=_GROUP)
             self._pending.append((flat, grads))
 
+    @staticmethod
+    def _scatter_back(flat, grads):
+        views, o = [], 0
+        for g in grads:
+            n = g.numel()
+            views.append(flat[o:o + n].view_as(g))
+            o += n
+        torch._foreach_copy_(grads, views)     # one multi-tensor kernel instead of one copy per parameter
+
     def wait(self):
         if not self._pending:
             return
@@ -145,29 +154,83 @@ class GradBuckets:
             cs = comm_stream()
             with torch.cuda.stream(cs):
                 for flat, grads in self._pending:
-                    o = 0
-                    for g in grads:
-                        n = g.numel()
-                        g.copy_(flat[o:o + n].view_as(g))
-                        o += n
+                    self._scatter_back(flat, grads)
             torch.cuda.current_stream().wait_stream(cs)
         else:
             for flat, grads in self._pending:
-                o = 0
-                for g in grads:
-                    n = g.numel()
-                    g.copy_(flat[o:o + n].view_as(g))
-                    o += n
+                self._scatter_back(flat, grads)
         self._pending.clear()
 
 
+class GradReducer:
+    """Overlaps the gradient all-reduce with the rest of the backward pass.
+
+    `buckets` is a list of parameter lists (one per network).  A post-accumulate-grad hook on every parameter
+    counts down its bucket; when the last gradient of a bucket has been written, the bucket's SUM all-reduce is
+    launched on the communication stream (GradBuckets.launch) while autograd keeps running BPTT for the
+    remaining networks.  arm() before backward, finish() after it (launches whatever did not fire, then joins).
+    Single process: every call is a no-op."""
+
+    def __init__(self, buckets):
+        self.buckets = [list(b) for b in buckets]
+        self.where = {}
+        self.armed = False
+        self.left = []
+        self.launched = []
+        self.gb = GradBuckets()
+        self.handles = []
+        for bi, b in enumerate(self.buckets):
+            for p in b:
+                self.where[id(p)] = bi
+                self.handles.append(p.register_post_accumulate_grad_hook(self._hook))
+
+    def arm(self):
+        self.armed = _ENABLED
+        self.left = [len(b) for b in self.buckets]
+        self.launched = [False] * len(self.buckets)
+
+    def _hook(self, p):
+        if not self.armed:
+            return
+        bi = self.where[id(p)]
+        self.left[bi] -= 1
+        if self.left[bi] == 0 and not self.launched[bi]:
+            self.launched[bi] = True
+            self.gb.launch(self.buckets[bi])
+
+    def finish(self):
+        if not self.armed:
+            return
+        for bi, b in enumerate(self.buckets):
+            if not self.launched[bi]:
+                self.launched[bi] = True
+                self.gb.launch(b)
+        self.gb.wait()
+        self.armed = False
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+
+
+_WARNED_RAGGED = False
+
+
 def shard_batch(x: torch.Tensor) -> torch.Tensor:
-    """Contiguous shard of a global batch for this rank (global batch must divide evenly; the DP sampler pads)."""
+    """Contiguous shard of a global batch for this rank.  Every rank must hold the same number of sequences
+    (allreduce_stats relies on it), so a ragged tail (n % world != 0, e.g. the last batch of an epoch with
+    drop_last=False, tt:33-37) is trimmed to the largest multiple of the world size."""
+    global _WARNED_RAGGED
     if not _ENABLED:
         return x
     w, r = world_size(), rank()
     n = x.shape[0]
-    if n % w != 0:
-        raise ValueError(f"global batch {n} is not divisible by world size {w}")
+    if n < w:
+        raise ValueError(f"global batch {n} is smaller than the world size {w}")
     per = n // w
+    if n % w != 0 and not _WARNED_RAGGED:
+        _WARNED_RAGGED = True
+        if r == 0:
+            print(f"timegan_b200.dist: global batch {n} not divisible by {w} ranks; using the first {per * w} sequences")
     return x[r * per:(r + 1) * per]

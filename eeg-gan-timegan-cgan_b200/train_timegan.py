@@ -187,9 +187,22 @@ def _zero_grads(opt):
     opt.zero_grad(set_to_none=True)
 
 
-def _reduce_and_step(opt, params, clip):
-    """DP: SUM-all-reduce the local gradient contributions (dist.py), then clip_grad_norm_ + Adam."""
-    if _dist.is_enabled():
+def _reducer(model, key: str, modules):
+    """Per-(model, parameter set) gradient reducer with one bucket per network (DP only; hooks are registered once)."""
+    if not _dist.is_enabled():
+        return None
+    cache = model.__dict__.setdefault("_tg_reducers", {})
+    if key not in cache:
+        cache[key] = _dist.GradReducer([list(m.parameters()) for m in modules])
+    return cache[key]
+
+
+def _reduce_and_step(opt, params, clip, reducer=None):
+    """DP: SUM-all-reduce the local gradient contributions (dist.py), then clip_grad_norm_ + Adam.  With a
+    reducer the buckets were launched from autograd hooks while BPTT was still running; here they are joined."""
+    if reducer is not None:
+        reducer.finish()
+    elif _dist.is_enabled():
         b = _dist.GradBuckets()
         b.launch(params)
         b.wait()
@@ -256,8 +269,11 @@ def phase_autoencoder(model: TimeGAN, loader: DataLoader, device, optER: optim.O
             x_tilde = model.reconstruct(x)
             loss = recon_loss(x, x_tilde)
             _zero_grads(optER)
+            red = _reducer(model, "ER", (model.recovery, model.embedder))
+            if red is not None:
+                red.arm()
             loss.backward()
-            _reduce_and_step(optER, params, clip)
+            _reduce_and_step(optER, params, clip, red)
             epoch_loss += loss.detach() * x_batch.size(0)
             n += x_batch.size(0)
         log(f"[AE] epoch {ep}/{epochs}  recon={epoch_loss.item() / n:.5f}")
@@ -278,8 +294,11 @@ def phase_supervisor(model: TimeGAN, loader: DataLoader, device, optS: optim.Opt
             h_pred = model.supervisor(h_in)
             loss = _losses.mse_loss(h_pred, h_tgt)
             _zero_grads(optS)
+            red = _reducer(model, "S", (model.supervisor,))
+            if red is not None:
+                red.arm()
             loss.backward()
-            _reduce_and_step(optS, params, clip)
+            _reduce_and_step(optS, params, clip, red)
             epoch_loss += loss.detach() * x_batch.size(0)
             n += x_batch.size(0)
         log(f"[SUP] epoch {ep}/{epochs}  sup={epoch_loss.item() / n:.5f}")
@@ -413,9 +432,14 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
 
     _zero_grads(optG)
+    # buckets in the order their BPTT finishes (recovery, embedder first; then supervisor, generator): each
+    # bucket's all-reduce overlaps the BPTT of the networks that are still running
+    red = _reducer(model, "G", (model.recovery, model.embedder, model.supervisor, model.generator))
+    if red is not None:
+        red.arm()
     g_total.backward()
     params = _params(model.generator, model.supervisor, model.embedder, model.recovery)
-    _reduce_and_step(optG, params, clip)
+    _reduce_and_step(optG, params, clip, red)
     nz.end()
     if schedulerG is not None:
         schedulerG.step()
@@ -483,7 +507,9 @@ class GraphedJointStep:
             if self.graph is None:
                 torch.cuda.synchronize(self.device)
                 self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
+                # thread_local: the autograd worker and (under DP) the NCCL watchdog issue CUDA calls from other
+                # threads while this thread captures
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                     self.out = self._joint()
             self.graph.replay()
             out = self.out

@@ -30,8 +30,9 @@ def _worker(rank, world, port, ret):
         w = torch.rand(3, generator=g).requires_grad_(True)  # a "parameter"
         xs = D.shard_batch(X)
         assert xs.shape[0] == 8 // world and torch.equal(xs, X[rank * 4:(rank + 1) * 4])
+        assert D.shard_batch(X[:7]).shape[0] == 3          # ragged tail trimmed to a multiple of the world size
         with pytest.raises(ValueError):
-            D.shard_batch(X[:7])
+            D.shard_batch(X[:1])
         # --- statistics all-reduce: sum + global count ---
         s, n = D.allreduce_stats(xs.sum((0, 1)), xs.shape[0] * xs.shape[1])
         assert n == 40 and torch.allclose(s, X.sum((0, 1)), atol=1e-6)
@@ -58,6 +59,23 @@ def _worker(rank, world, port, ret):
         allp = [torch.rand(4, 1, generator=torch.Generator().manual_seed(10 + r)) for r in range(world)]
         assert torch.allclose(gm.detach(), torch.cat(allp).mean(), atol=1e-6)
         assert torch.allclose(p.grad, torch.full_like(p, 1.0 / (4 * world)))
+        # --- hook-driven bucketed reducer: buckets fire as soon as their last gradient lands ---
+        lin1, lin2 = torch.nn.Linear(3, 4), torch.nn.Linear(4, 2)
+        with torch.no_grad():
+            for q in list(lin1.parameters()) + list(lin2.parameters()):
+                q.copy_(torch.rand(q.shape, generator=torch.Generator().manual_seed(int(q.numel()))))
+        red = D.GradReducer([list(lin2.parameters()), list(lin1.parameters())])
+        red.arm()
+        out = lin2(torch.tanh(lin1(xs))).sum() / (40 * 2)          # local contribution to the global mean
+        out.backward()
+        assert red.launched == [True, True]                          # both fired from the hooks, before finish()
+        red.finish()
+        ref1, ref2 = torch.nn.Linear(3, 4), torch.nn.Linear(4, 2)
+        ref1.load_state_dict(lin1.state_dict()); ref2.load_state_dict(lin2.state_dict())
+        (ref2(torch.tanh(ref1(X))).sum() / (40 * 2)).backward()
+        for a, b in zip(list(lin1.parameters()) + list(lin2.parameters()), list(ref1.parameters()) + list(ref2.parameters())):
+            assert torch.allclose(a.grad, b.grad, atol=1e-6)
+        red.remove()
         ret[rank] = "ok"
     finally:
         D.disable()
