@@ -44,9 +44,9 @@ SIGNATURES = {
     "tg_wgrad_gru_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tg_wgrad_gru": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _i]),
     "tg_gru_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
-    "tg_gru_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "tg_gru_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tg_gru_jvp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
-    "tg_gru_jvp_bwd": (_i, [_vp] * 14 + [_i, _i, _i, _i]),
+    "tg_gru_jvp_bwd": (_i, [_vp] * 14 + [_i, _i, _i, _i, _vp]),
     "tg_reduce_workspace_bytes": (_sz, []),
     "tg_sqdiff_sum": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, _sz]),
     "tg_scaled_diff": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i]),

@@ -208,9 +208,9 @@ int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, fl
 }
 
 int tg_gru_bwd(void* stream, const float* dy, const float* rzn, const float* q, const float* y, const float* w_hh,
-               float* dgi, float* dq, int B, int T, int H, int flags) {
+               float* dgi, float* dq, int B, int T, int H, int flags, const float* w_hh_t) {
   ProfScope _ps(stream, K_GRU_BWD, (double)B * T * H * ((flags & TG_GRU_DY_LAST) ? 36.0 : 40.0), 6.0 * B * T * (double)H * H);
-  return tg_gru_bwd_impl((cudaStream_t)stream, dy, rzn, q, y, w_hh, dgi, dq, B, T, H, flags);
+  return tg_gru_bwd_impl((cudaStream_t)stream, dy, rzn, q, y, w_hh, dgi, dq, B, T, H, flags, w_hh_t);
 }
 
 int tg_gru_jvp_fwd(void* stream, float* gid, const float* rzn, const float* q, const float* y, const float* w_hh,
@@ -221,10 +221,11 @@ int tg_gru_jvp_fwd(void* stream, float* gid, const float* rzn, const float* q, c
 
 int tg_gru_jvp_bwd(void* stream, const float* hbar, const float* hdbar, const float* rzn, const float* q,
                    const float* ta, const float* qdot, const float* y, const float* ydot, const float* w_hh,
-                   float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags) {
+                   float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags,
+                   const float* w_hh_t) {
   ProfScope _ps(stream, K_JVP_BWD, (double)B * T * H * 104.0, 12.0 * B * T * (double)H * H);
   return tg_gru_jvp_bwd_impl((cudaStream_t)stream, hbar, hdbar, rzn, q, ta, qdot, y, ydot, w_hh, gib, qb, gidb, qdb, B,
-                             T, H, flags);
+                             T, H, flags, w_hh_t);
 }
 
 size_t tg_reduce_workspace_bytes(void) { return tg_reduce_ws_bytes(); }

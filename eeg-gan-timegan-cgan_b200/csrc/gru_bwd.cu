@@ -210,10 +210,13 @@ int dispatch_bt(cudaStream_t st, const BwdParams& p, int bt) {
 }  // namespace
 
 int tg_gru_bwd_impl(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y,
-                    const float* whh, float* dgi, float* dq, int B, int T, int H, int flags) {
+                    const float* whh, float* dgi, float* dq, int B, int T, int H, int flags, const float* whh_t) {
   TG_REQUIRE(dy && rzn && q && y && whh && dgi && dq, TG_ERR_ARG, "gru_bwd: null pointer");
   TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_bwd: bad shape B=%d T=%d H=%d", B, T, H);
-  TG_REQUIRE(H <= 128, TG_ERR_UNSUPPORTED, "gru_bwd: hidden size %d > 128 needs the cluster kernel (not built yet)", H);
+  if (H > 128) {
+    TG_REQUIRE(whh_t, TG_ERR_ARG, "gru_bwd: hidden size %d > 128 needs the transposed weight (w_hh_t)", H);
+    return tg_bigh_bwd(st, dy, rzn, q, y, whh_t, dgi, dq, B, T, H, (flags & TG_GRU_DY_LAST) ? 1 : 0);
+  }
   BwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, H, (flags & TG_GRU_DY_LAST) ? 1 : 0, 0};
   p.bulk = (H % 4 == 0) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(y) && tg_aligned16(dgi) &&
            tg_aligned16(dq) && (p.dy_last || tg_aligned16(dy)) && !(flags & TG_GRU_NO_BULK);

@@ -255,9 +255,10 @@ int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* b
                     int H, int flags) {
   TG_REQUIRE(gi && whh && bhh && y, TG_ERR_ARG, "gru_fwd: null pointer");
   TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_fwd: bad shape B=%d T=%d H=%d", B, T, H);
-  TG_REQUIRE(H <= 128, TG_ERR_UNSUPPORTED, "gru_fwd: hidden size %d > 128 needs the cluster kernel (not built yet)", H);
+  TG_REQUIRE(H <= 1024, TG_ERR_UNSUPPORTED, "gru_fwd: hidden size %d > 1024", H);
   const int save = (flags & TG_GRU_SAVE) ? 1 : 0;
   TG_REQUIRE(!save || q, TG_ERR_ARG, "gru_fwd: save requested without q buffer");
+  if (H > 128) return tg_bigh_fwd(st, gi, whh, bhh, y, q, B, T, H, save);
   FwdParams p{gi, whh, bhh, y, q, B, T, H, save, 0};
   p.bulk = (H % 4 == 0) && tg_aligned16(gi) && tg_aligned16(y) && (!save || tg_aligned16(q)) &&
            !(flags & TG_GRU_NO_BULK);

@@ -414,7 +414,7 @@ int tg_gru_jvp_fwd_impl(cudaStream_t st, float* gid, const float* rzn, const flo
                         const float* whh, float* ydot, float* qdot, int B, int T, int H, int flags) {
   TG_REQUIRE(gid && rzn && q && y && whh && ydot && qdot, TG_ERR_ARG, "gru_jvp_fwd: null pointer");
   TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_jvp_fwd: bad shape B=%d T=%d H=%d", B, T, H);
-  TG_REQUIRE(H <= 128, TG_ERR_UNSUPPORTED, "gru_jvp_fwd: hidden size %d > 128 unsupported", H);
+  if (H > 128) return tg_bigh_jvp_fwd(st, gid, rzn, q, y, whh, ydot, qdot, B, T, H);
   JfParams p{gid, rzn, q, y, whh, ydot, qdot, B, T, H, 0};
   p.bulk = (H % 4 == 0) && tg_aligned16(gid) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(y) &&
            tg_aligned16(ydot) && tg_aligned16(qdot) && !(flags & TG_GRU_NO_BULK);
@@ -426,11 +426,16 @@ int tg_gru_jvp_fwd_impl(cudaStream_t st, float* gid, const float* rzn, const flo
 
 int tg_gru_jvp_bwd_impl(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
                         const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh,
-                        float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags) {
+                        float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags,
+                        const float* whh_t) {
   TG_REQUIRE(hbar && hdbar && rzn && q && ta && qdot && y && ydot && whh && gib && qb && gidb && qdb, TG_ERR_ARG,
              "gru_jvp_bwd: null pointer");
   TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_jvp_bwd: bad shape B=%d T=%d H=%d", B, T, H);
-  TG_REQUIRE(H <= 128, TG_ERR_UNSUPPORTED, "gru_jvp_bwd: hidden size %d > 128 unsupported", H);
+  if (H > 128) {
+    TG_REQUIRE(whh_t, TG_ERR_ARG, "gru_jvp_bwd: hidden size %d > 128 needs the transposed weight (w_hh_t)", H);
+    return tg_bigh_jvp_bwd(st, hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh_t, gib, qb, gidb, qdb, B, T, H,
+                           (flags & TG_GRU_DY_LAST) ? 1 : 0);
+  }
   JbParams p{hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, H,
              (flags & TG_GRU_DY_LAST) ? 1 : 0, 0};
   p.bulk = (H % 4 == 0) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(ta) && tg_aligned16(qdot) &&

@@ -15,12 +15,24 @@ int tg_pick_bt(int B, int HP, int bt_override);
 int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T,
                     int H, int flags);
 int tg_gru_bwd_impl(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y,
-                    const float* whh, float* dgi, float* dq, int B, int T, int H, int flags);
+                    const float* whh, float* dgi, float* dq, int B, int T, int H, int flags, const float* whh_t);
 int tg_gru_jvp_fwd_impl(cudaStream_t st, float* gid, const float* rzn, const float* q, const float* y,
                         const float* whh, float* ydot, float* qdot, int B, int T, int H, int flags);
 int tg_gru_jvp_bwd_impl(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
                         const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh,
-                        float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags);
+                        float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags,
+                        const float* whh_t);
+
+// capacity fallback for H > 128 (gru_bigh.cu): W_hh streamed from L2 every step
+int tg_bigh_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T, int H,
+                int save);
+int tg_bigh_bwd(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y, const float* whh_t,
+                float* dgi, float* dq, int B, int T, int H, int dy_last);
+int tg_bigh_jvp_fwd(cudaStream_t st, float* gid, const float* rzn, const float* q, const float* y, const float* whh,
+                    float* ydot, float* qdot, int B, int T, int H);
+int tg_bigh_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
+                    const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh_t,
+                    float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only);
 
 // time-batched contractions (FFMA baseline path; fp32 exact)
 int tg_gemm_nt_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,

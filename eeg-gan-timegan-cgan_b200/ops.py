@@ -201,8 +201,9 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
         I = w_ih.shape[1]
         dgi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
         dq = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        w_hh_t = w_hh.t().contiguous() if H > 128 else None      # the H > 128 fallback walks W_hh^T rows
         check(lib.tg_gru_bwd(stream_ptr(), ptr(d), ptr(sv.rzn), ptr(sv.q), ptr(sv.y), ptr(w_hh), ptr(dgi), ptr(dq),
-                             B, T, H, _flags(_lib.GRU_DY_LAST if last_only else 0)), "tg_gru_bwd")
+                             B, T, H, _flags(_lib.GRU_DY_LAST if last_only else 0), ptr(w_hh_t)), "tg_gru_bwd")
         last_only = False
         dgi2 = dgi.view(B * T, 3 * H)
         if need_dw:
@@ -270,9 +271,10 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
         gidb = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
         qb = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         qdb = torch.empty(B, T, H, dtype=torch.float32, device=dev)
+        w_hh_t = w_hh.t().contiguous() if H > 128 else None
         check(lib.tg_gru_jvp_bwd(stream_ptr(), ptr(hb), ptr(hdb), ptr(sv.rzn), ptr(sv.q), ptr(ts.ta), ptr(ts.qdot),
                                  ptr(sv.y), ptr(ts.ydot), ptr(w_hh), ptr(gib), ptr(qb), ptr(gidb), ptr(qdb), B, T, H,
-                                 _flags(_lib.GRU_DY_LAST if last_only else 0)), "tg_gru_jvp_bwd")
+                                 _flags(_lib.GRU_DY_LAST if last_only else 0), ptr(w_hh_t)), "tg_gru_jvp_bwd")
         last_only = False
         g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
         gib2, gidb2 = gib.view(B * T, 3 * H), gidb.view(B * T, 3 * H)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 3
+#define TG_ABI_VERSION 4
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -87,6 +87,8 @@ int tg_wgrad_gru(void* stream, const float* dgi, const float* dq, const float* x
                  size_t ws_bytes, int mode /* TG_PROJ_* */);
 
 /* ---- persistent fused GRU layer forward (timegan_model.py:32-34 -> nn.GRU per-timestep loop) --------------
+ * H <= 128: W_hh register-resident (gru_fwd.cu ...); 128 < H <= 1024: capacity fallback that streams W_hh from L2
+ * every step (gru_bigh.cu; H % 4 == 0).
  * gi (B,T,3H) holds X W_ih^T + b_ih on entry; with TG_GRU_SAVE it holds r,z,n on exit and q (B,T,H) receives
  * h_{t-1} W_hn^T + b_hn.  y (B,T,H) receives h_t.  h0 = 0 (the reference never passes an initial state). */
 int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, float* y, float* q, int B, int T, int H,
@@ -96,7 +98,8 @@ int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, fl
  * in: dy (B,T,H) [or (B,H) with TG_GRU_DY_LAST], saved rzn,q, layer output y.  out: dgi (B,T,3H) =
  * [dar,daz,dan] (gradient of gi; also rows 0..2H of dGH) and dq (B,T,H) = dan*r (rows 2H..3H of dGH). */
 int tg_gru_bwd(void* stream, const float* dy, const float* rzn, const float* q, const float* y, const float* w_hh,
-               float* dgi, float* dq, int B, int T, int H, int flags);
+               float* dgi, float* dq, int B, int T, int H, int flags,
+               const float* w_hh_t /* (H,3H) = w_hh transposed; only read (and required) when H > 128 */);
 
 /* ---- R1 penalty (train_timegan.py:198-202) without generic double backward: tangent forward ... ----------
  * gid (B,T,3H) holds xdot W_ih^T on entry and the tangent pre-activations a_r,a_z,a_n on exit. */
@@ -106,7 +109,8 @@ int tg_gru_jvp_fwd(void* stream, float* gid, const float* rzn, const float* q, c
  * adjoints of the primal (gib,qb) and tangent (gidb,qdb) gate pre-activations, laid out like dgi/dq. */
 int tg_gru_jvp_bwd(void* stream, const float* hbar, const float* hdbar, const float* rzn, const float* q,
                    const float* ta, const float* qdot, const float* y, const float* ydot, const float* w_hh,
-                   float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags);
+                   float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int flags,
+                   const float* w_hh_t /* as for tg_gru_bwd */);
 
 /* ---- losses (train_timegan.py:72-74 recon, :156-158 sup MSE, :79-80 first difference, :82-126 cov/ACF) ----
  * Scalars live on the device (float*), so no host synchronisation is needed between kernels. */

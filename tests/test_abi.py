@@ -31,7 +31,7 @@ def test_argument_errors_are_reported_not_crashed():
     from timegan_b200 import _lib
     rc = _lib.lib.tg_gru_fwd(None, None, None, None, None, None, 1, 1, 1, 0)
     assert rc < 0 and "null" in _lib.last_error()
-    rc = _lib.lib.tg_gru_fwd(None, 16, 16, 16, 16, None, 1, 1, 300, 0)   # pointers are never dereferenced on the host
+    rc = _lib.lib.tg_gru_fwd(None, 16, 16, 16, 16, None, 1, 1, 3000, 0)   # pointers are never dereferenced on the host
     assert rc < 0 and "hidden size" in _lib.last_error()
     with pytest.raises(RuntimeError, match="argument error"):
         _lib.check(rc, "tg_gru_fwd")

@@ -21,6 +21,8 @@ SHAPES = [
     (7, 768, 24, 24, 3),     # ragged batch (N % B != 0 tail)
     (9, 200, 14, 64, 3),     # config c2 dims
     (3, 96, 14, 128, 2),     # config c3 dims
+    (5, 40, 14, 160, 2),     # H > 128: capacity fallback (W_hh streamed from L2)
+    (6, 24, 14, 256, 2),     # config c4's H = 256 point
 ]
 
 
@@ -129,7 +131,8 @@ def test_autograd_function_module_api():
         assert relerr(p.grad, q.grad) < TOL, n
 
 
-@pytest.mark.parametrize("B,T,I,H,L", [(3, 12, 5, 8, 2), (4, 64, 24, 24, 3), (2, 30, 14, 64, 1), (2, 20, 14, 128, 2)])
+@pytest.mark.parametrize("B,T,I,H,L", [(3, 12, 5, 8, 2), (4, 64, 24, 24, 3), (2, 30, 14, 64, 1), (2, 20, 14, 128, 2),
+                                       (5, 16, 14, 256, 2)])
 def test_tangent_forward_and_reverse_match_oracle(B, T, I, H, L):
     """R1 building blocks (train_timegan.py:198-202 restated per SURVEY.md A.4) vs oracle/gru_math.py in fp64."""
     from oracle import gru_math as gm

@@ -72,6 +72,7 @@ def test_steps_match_reference_golden(case):
     (14, 28, 56, 1, 5, 200, 1.0, 0.23, 0.03, 0.02, 48, 0.25),   # timegan_config.json values
     (14, 16, 16, 2, 6, 64, 0.0, 0.0, 0.0, 0.0, 8, 0.0),          # every optional term off
     (14, 64, 64, 3, 3, 64, 2.5, 0.15, 0.1, 0.1, 16, 0.1),        # config c2 dims
+    (14, 256, 256, 2, 5, 24, 1.0, 0.15, 0.05, 0.05, 8, 0.2),     # config c4's H = 256 point (capacity fallback)
 ])
 def test_joint_steps_match_oracle_port_live(cfg):
     """Three consecutive D+G updates from identical weights and identical (replayed) noise."""
