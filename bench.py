@@ -209,9 +209,10 @@ def run_ours(a):
     torch.manual_seed(42)
     model = tg.TimeGAN(X_DIM, a.hidden, a.hidden, a.layers, 0.0).to(dev)
     P = tt._params
-    # CUDA-graph replay is used on one GPU; under data parallelism the step is issued eagerly (capturing the NCCL
-    # all-reduces together with the side-stream forks hung in round 1 -- to be revisited)
-    use_graph = (not a.no_graph) and (world == 1 or a.dp_graph)
+    # CUDA-graph replay everywhere: under data parallelism the gradient / statistics all-reduces are this
+    # package's own peer-memory kernels (csrc/peer_allreduce.cu), which are ordinary launches and replay with the
+    # rest of the step.  TIMEGAN_B200_COMM=nccl falls back to eagerly issued NCCL collectives.
+    use_graph = (not a.no_graph) and (world == 1 or tdist.peer_comm() is not None or a.dp_graph)
     optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"], capturable=use_graph)
     optG = tg.FusedAdam(P(model.generator, model.supervisor, model.embedder, model.recovery), lr=HP["lr_g"],
                         betas=HP["betas"], capturable=use_graph)
@@ -315,6 +316,8 @@ def run_ours(a):
     else:
         prof_steps = a.steps
 
+    if tdist.peer_comm() is not None:
+        tdist.peer_comm().check_status()
     if world > 1:
         td.destroy_process_group()
     if rank != 0:
@@ -346,6 +349,8 @@ def run_ours(a):
                 "ms_per_step": round(ms_e2e / a.steps, 3)},
         "gpu_launches": int(round(launches_per_step * a.steps)),
         "issue": "cuda-graph replay (1 graph launch per step)" if use_graph else "eager",
+        "comm": (None if world == 1 else "peer-memory all-reduce kernels over NVLink (csrc/peer_allreduce.cu)"
+                 if tdist.peer_comm() is not None else "NCCL all_reduce"),
         "host_issue_ms_per_step": round(host_issue_ms / a.steps, 3),
         "clocks": clk,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": hbm_peak, "unit": "GB/s",

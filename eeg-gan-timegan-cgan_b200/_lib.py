@@ -64,6 +64,14 @@ SIGNATURES = {
                      _f, _f, _f, _f, _f, _i, _f, _vp]),
     "tg_rng_uniform": (_i, [_vp, _vp, _ll, _ull, _ull, _f, _f, _vp]),
     "tg_rng_add_normal": (_i, [_vp, _vp, _vp, _ll, _f, _ull, _ull, _vp]),
+    "tg_peer_chunk_floats": (_i, []),
+    "tg_peer_alloc": (_i, [C.POINTER(_vp), _sz]),
+    "tg_peer_free": (_i, [_vp]),
+    "tg_peer_export": (_i, [_vp, C.c_char_p]),
+    "tg_peer_open": (_i, [C.c_char_p, C.POINTER(_vp)]),
+    "tg_peer_close": (_i, [_vp]),
+    "tg_peer_site_bytes": (_sz, [_i, C.POINTER(_ll), _i, C.POINTER(_sz)]),
+    "tg_peer_allreduce": (_i, [_vp, _i, _i, C.POINTER(_vp), _sz, _sz, _vp, _vp, _i, C.POINTER(_vp), C.POINTER(_ll)]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

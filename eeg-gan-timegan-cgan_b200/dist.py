@@ -21,6 +21,7 @@ import torch.distributed as td
 _GROUP = None          # process group in use (None = single process)
 _ENABLED = False
 _COMM_STREAM = None    # side stream for gradient buckets
+_PEER = None           # PeerComm: all-reduce kernels over NVLink peer memory (CUDA ranks of one box)
 
 
 def init(backend: Optional[str] = None, device: Optional[torch.device] = None):
@@ -39,7 +40,32 @@ def init(backend: Optional[str] = None, device: Optional[torch.device] = None):
         td.init_process_group(backend=backend, **kw)
     _GROUP = td.group.WORLD
     _ENABLED = True
+    if backend == "nccl" and device is not None and os.environ.get("TIMEGAN_B200_COMM", "peer") == "peer":
+        enable_peer(device)
     return td.get_rank(), td.get_world_size()
+
+
+def enable_peer(device, region_mb: Optional[int] = None):
+    """Route every all-reduce of this package through csrc/peer_allreduce.cu (one multi-tensor kernel per bucket
+    over NVLink peer memory, graph-capturable) instead of torch.distributed.  The process group stays in use for
+    the rendezvous (IPC handle exchange) and barriers.  TIMEGAN_B200_COMM=nccl keeps the NCCL path."""
+    global _PEER
+    if _PEER is None:
+        mb = int(region_mb or os.environ.get("TIMEGAN_B200_PEER_MB", "256"))
+        _PEER = PeerComm(torch.device(device), _GROUP, mb << 20)
+    return _PEER
+
+
+def peer_comm():
+    return _PEER
+
+
+def begin_step(tag: str):
+    """Start of one optimiser step (`tag` names the step function).  The k-th all-reduce issued after
+    begin_step(tag) is the same call site in every step and on every rank -- that is what lets the peer
+    all-reduce keep one staging area / flag set / replay counter per site."""
+    if _PEER is not None:
+        _PEER.begin_step(tag)
 
 
 def enable(group=None):
@@ -50,6 +76,7 @@ def enable(group=None):
 
 
 def disable():
+    """Back to single-process behaviour.  The peer region (if any) stays mapped; enable() re-activates it."""
     global _GROUP, _ENABLED, _COMM_STREAM
     _GROUP, _ENABLED, _COMM_STREAM = None, False, None
 
@@ -76,7 +103,10 @@ def allreduce_stats(t: torch.Tensor, count) -> Tuple[torch.Tensor, float]:
     if not _ENABLED:
         return t, float(count)
     buf = t.detach().clone().contiguous()
-    td.all_reduce(buf, op=td.ReduceOp.SUM, group=_GROUP)
+    if _PEER is not None and buf.is_cuda:
+        _PEER.allreduce_([buf])
+    else:
+        td.all_reduce(buf, op=td.ReduceOp.SUM, group=_GROUP)
     return buf, float(count) * world_size()
 
 
@@ -106,6 +136,97 @@ def comm_stream() -> "torch.cuda.Stream":
     return _COMM_STREAM
 
 
+class PeerComm:
+    """Host side of csrc/peer_allreduce.cu for the ranks of ONE box.
+
+    Every rank cudaMallocs one region, the 64-byte IPC handles travel through the process group once, and from
+    then on an all-reduce is one kernel launch on the current stream.  Region layout (identical on every rank):
+    [flag words | staging areas]; a call site -- key (step tag, index of the call within the step, tensor
+    sizes) -- gets its slice of both on first use, plus a local {epoch, counter} pair in `self.epochs`."""
+
+    FLAG_BYTES = 4 << 20
+    MAX_SITES = 1024
+
+    def __init__(self, device: torch.device, group, region_bytes: int):
+        import ctypes as C
+        from ._lib import lib, check
+        self._C, self._lib, self._check = C, lib, check
+        self.device = device
+        self.group = group
+        self.rank, self.world = td.get_rank(group), td.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("peer all-reduce covers the (<= 8) GPUs of one NVSwitch box")
+        self.region_bytes = int(region_bytes)
+        with torch.cuda.device(device):
+            own = C.c_void_p()
+            check(lib.tg_peer_alloc(C.byref(own), self.region_bytes), "tg_peer_alloc")
+            handle = C.create_string_buffer(64)
+            check(lib.tg_peer_export(own, handle), "tg_peer_export")
+            handles = [None] * self.world
+            td.all_gather_object(handles, handle.raw, group=group)
+            self.regions = (C.c_void_p * self.world)()
+            self._own = own
+            for r in range(self.world):
+                if r == self.rank:
+                    self.regions[r] = own.value
+                else:
+                    peer = C.c_void_p()
+                    check(lib.tg_peer_open(handles[r], C.byref(peer)), f"tg_peer_open(rank {r})")
+                    self.regions[r] = peer.value
+        td.barrier(group=group)
+        self.epochs = torch.zeros(self.MAX_SITES, 2, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.sites = {}
+        self.flag_cursor, self.data_cursor = 0, self.FLAG_BYTES
+        self.tag, self.k = "", 0
+        self.chunk = int(lib.tg_peer_chunk_floats())
+
+    def begin_step(self, tag: str):
+        self.tag, self.k = tag, 0
+
+    def _site(self, sizes):
+        C = self._C
+        key = (self.tag, self.k, tuple(sizes))
+        self.k += 1
+        st = self.sites.get(key)
+        if st is None:
+            arr = (C.c_longlong * len(sizes))(*sizes)
+            fb = C.c_size_t()
+            db = int(self._lib.tg_peer_site_bytes(len(sizes), arr, self.world, C.byref(fb)))
+            fb = (int(fb.value) + 255) // 256 * 256
+            if len(self.sites) >= self.MAX_SITES or self.flag_cursor + fb > self.FLAG_BYTES or \
+                    self.data_cursor + db > self.region_bytes:
+                raise RuntimeError(
+                    f"peer region exhausted ({len(self.sites)} call sites, {self.data_cursor + db} of "
+                    f"{self.region_bytes} B): call dist.begin_step() once per optimiser step, or raise "
+                    "TIMEGAN_B200_PEER_MB")
+            st = dict(idx=len(self.sites), data_off=self.data_cursor, flag_off=self.flag_cursor, sizes=arr)
+            self.flag_cursor += fb
+            self.data_cursor += (db + 255) // 256 * 256
+            self.sites[key] = st
+        return st
+
+    def allreduce_(self, tensors):
+        """SUM `tensors` (contiguous fp32 CUDA tensors) in place across the ranks, on the current stream."""
+        C = self._C
+        for i0 in range(0, len(tensors), 48):
+            group = tensors[i0:i0 + 48]
+            for t in group:
+                if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                    raise RuntimeError("peer all-reduce needs contiguous fp32 CUDA tensors")
+            st = self._site([t.numel() for t in group])
+            ptrs = (C.c_void_p * len(group))(*[t.data_ptr() for t in group])
+            self._check(self._lib.tg_peer_allreduce(
+                torch.cuda.current_stream().cuda_stream, self.rank, self.world, self.regions, st["data_off"],
+                st["flag_off"], self.epochs[st["idx"]].data_ptr(), self.status.data_ptr(), len(group), ptrs,
+                st["sizes"]), "tg_peer_allreduce")
+
+    def check_status(self):
+        """Raises if a kernel gave up waiting for a peer (synchronises)."""
+        if int(self.status.item()) != 0:
+            raise RuntimeError("peer all-reduce timed out waiting for another rank")
+
+
 class GradBuckets:
     """Bucketed SUM all-reduce of parameter gradients on a side stream.
 
@@ -123,7 +244,17 @@ class GradBuckets:
         grads = [p.grad for p in params if p.grad is not None]
         if not grads:
             return
-        if grads[0].is_cuda:
+        if grads[0].is_cuda and _PEER is not None:
+            # one multi-tensor kernel: gathers the gradients out of their own tensors, exchanges them over NVLink
+            # peer memory and writes the sums back in place -- nothing to flatten or scatter back
+            cs = comm_stream()
+            cs.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cs):
+                _PEER.allreduce_(grads)
+                for g in grads:
+                    g.record_stream(cs)
+            self._pending.append((None, grads))
+        elif grads[0].is_cuda:
             cs = comm_stream()
             cs.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(cs):
@@ -149,12 +280,13 @@ class GradBuckets:
     def wait(self):
         if not self._pending:
             return
-        cuda = self._pending[0][0].is_cuda
+        cuda = self._pending[0][1][0].is_cuda
         if cuda:
             cs = comm_stream()
             with torch.cuda.stream(cs):
                 for flat, grads in self._pending:
-                    self._scatter_back(flat, grads)
+                    if flat is not None:
+                        self._scatter_back(flat, grads)
             torch.cuda.current_stream().wait_stream(cs)
         else:
             for flat, grads in self._pending:

@@ -266,6 +266,7 @@ def phase_autoencoder(model: TimeGAN, loader: DataLoader, device, optER: optim.O
         n = 0
         for (x_batch,) in loader:
             x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+            _dist.begin_step("AE")
             x_tilde = model.reconstruct(x)
             loss = recon_loss(x, x_tilde)
             _zero_grads(optER)
@@ -288,6 +289,7 @@ def phase_supervisor(model: TimeGAN, loader: DataLoader, device, optS: optim.Opt
         n = 0
         for (x_batch,) in loader:
             x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+            _dist.begin_step("SUP")
             with torch.no_grad():
                 h = model.encode(x)
             h_in, h_tgt = h[:, :-1, :].contiguous(), h[:, 1:, :].contiguous()
@@ -309,6 +311,7 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
     """Discriminator update with R1 and the soft throttle (tt:166-225).  Returns (loss, acc)."""
     D = model.discriminator
     D.train()
+    _dist.begin_step("D")
     nz = _noise_source(noise, device)
     nz.begin()
     B, T = x.size(0), x.size(1)
@@ -404,6 +407,7 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
              sync: bool = True):
     """Generator/supervisor/embedder/recovery update (tt:228-276).  Returns the six logged losses."""
     model.generator.train(); model.supervisor.train(); model.embedder.train(); model.recovery.train()
+    _dist.begin_step("G")
     nz = _noise_source(noise, device)
     nz.begin()
     B, T = x.size(0), x.size(1)
@@ -597,7 +601,9 @@ def train_single_npz(npz_path: Path, out_dir: Path,
     optS = FusedAdam(model.supervisor.parameters(), lr=lr_g, betas=betas)
     phase_supervisor(model, loader, device, optS, grad_clip, sup_epochs, LOG)
 
-    use_graph = bool(graph) and nz is None and not _dist.is_enabled()
+    # under data parallelism the step can only be captured when the all-reduces are this package's own peer-memory
+    # kernels (dist.PeerComm); NCCL collectives are issued eagerly
+    use_graph = bool(graph) and nz is None and (not _dist.is_enabled() or _dist.peer_comm() is not None)
     optD = FusedAdam(model.discriminator.parameters(), lr=lr_d, betas=betas, capturable=use_graph)
     optG = FusedAdam(_params(model.generator, model.supervisor, model.embedder, model.recovery), lr=lr_g, betas=betas,
                      capturable=use_graph)
@@ -651,7 +657,7 @@ def train_single_npz(npz_path: Path, out_dir: Path,
             (x_batch,) = next(loader_iter)
         x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
 
-        if graphed is not None and x.shape[0] == batch_size and inst_noise > 0:
+        if graphed is not None and x.shape[0] == batch_size // _dist.world_size() and inst_noise > 0:
             vals = graphed(x, inst_noise).clone()           # the graph's output buffer is reused by the next replay
             pending.append((step, tuple(vals.unbind(0))))
         else:

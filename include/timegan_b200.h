@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 4
+#define TG_ABI_VERSION 5
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -150,6 +150,29 @@ int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long see
                    float hi, const unsigned long long* ctr /* NULL or device counter added to offset */);
 int tg_rng_add_normal(void* stream, const float* in /* may be NULL */, float* out, long long n, float std,
                       unsigned long long seed, unsigned long long offset, const unsigned long long* ctr);
+
+/* ---- data-parallel all-reduce over NVLink peer memory (net-new: the reference is single-process; replaces the
+ * torch.distributed all_reduce a DDP port of train_timegan.py:141,160,220,268 would issue) ------------------
+ * Every rank owns one "peer region" (tg_peer_alloc: cudaMalloc'd + zeroed, the only device memory this library
+ * allocates, because CUDA IPC needs a base allocation), exports it (64-byte cudaIpcMemHandle_t), and maps the
+ * regions of the other ranks of the box (tg_peer_open).  tg_peer_allreduce SUMs n tensors IN PLACE across
+ * `world` ranks in ONE ordinary kernel launch (graph-capturable, no host synchronisation): `regions[r]` is rank
+ * r's region as seen from this process; data_off / flag_off locate this call site's staging area
+ * (tg_peer_site_bytes) and flag words inside every region -- identical offsets on all ranks; `epoch` and
+ * `status` are caller-owned LOCAL device words (the call site's replay counter and a peer-timeout flag).  All ranks must issue the same call sites with the same
+ * tensor sizes; the sums are bit-identical on every rank. */
+#define TG_PEER_MAX 8
+int tg_peer_chunk_floats(void);
+int tg_peer_alloc(void** ptr, size_t bytes);
+int tg_peer_free(void* ptr);
+int tg_peer_export(void* ptr, unsigned char* handle64);
+int tg_peer_open(const unsigned char* handle64, void** peer_ptr);
+int tg_peer_close(void* peer_ptr);
+size_t tg_peer_site_bytes(int n, const long long* sizes, int world, size_t* flag_bytes);
+int tg_peer_allreduce(void* stream, int rank, int world, void* const* regions, size_t data_off, size_t flag_off,
+                      unsigned int* epoch /* device uint32[2], zero-initialised, one per call site */,
+                      unsigned int* status /* device uint32 error word */, int n, float* const* tensors,
+                      const long long* sizes);
 
 #ifdef __cplusplus
 }

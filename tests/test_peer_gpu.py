@@ -1,0 +1,45 @@
+"""Peer-memory all-reduce (csrc/peer_allreduce.cu): host-side checks everywhere, the kernel itself on >= 2 GPUs."""
+import ctypes as C
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_peer_site_sizes_and_argument_checks():
+    from timegan_b200 import _lib
+    lib = _lib.lib
+    chunk = lib.tg_peer_chunk_floats()
+    assert chunk == 4096
+    sizes = (C.c_longlong * 3)(1, chunk, chunk + 1)           # 1 + 1 + 2 chunks
+    fb = C.c_size_t()
+    db = lib.tg_peer_site_bytes(3, sizes, 8, C.byref(fb))
+    assert db == 2 * 4 * chunk * 4 and fb.value == 4 * 8 * 4
+    regions = (C.c_void_p * 2)(256, 256)
+    ptrs = (C.c_void_p * 1)(256)
+    one = (C.c_longlong * 1)(16)
+    # never launches: every argument error is caught on the host
+    assert lib.tg_peer_allreduce(None, 0, 1, regions, 0, 0, 256, 256, 1, ptrs, one) < 0       # world < 2
+    assert "rank/world" in _lib.last_error()
+    assert lib.tg_peer_allreduce(None, 0, 9, regions, 0, 0, 256, 256, 1, ptrs, one) < 0       # > 8 ranks
+    assert lib.tg_peer_allreduce(None, 0, 2, regions, 0, 0, None, 256, 1, ptrs, one) < 0      # no epoch word
+    assert lib.tg_peer_allreduce(None, 0, 2, regions, 8, 0, 256, 256, 1, ptrs, one) < 0       # misaligned staging
+    assert "misaligned" in _lib.last_error()
+    assert lib.tg_peer_allreduce(None, 0, 2, regions, 0, 0, 256, 256, 49, ptrs, one) < 0      # too many tensors
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box")
+def test_peer_allreduce_matches_nccl_two_ranks():
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        str(ROOT / "tools" / "check_peer_allreduce.py")], capture_output=True, text=True, env=env,
+                       timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count(": OK") == 2
