@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dp-graph", action="store_true", help="experimental: capture the NCCL all-reduces too (N > 1)")
     ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
+    ap.add_argument("--bt", type=int, default=0, choices=[0, 1, 2, 4],
+                    help="sequences per CTA in the recurrent kernels (0 = the library's heuristic)")
     return ap.parse_args()
 
 
@@ -204,6 +206,7 @@ def run_ours(a):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/null")   # keep NCCL's version banner off stdout (one JSON line)
         tdist.init(backend="nccl", device=dev)
     ops.set_proj_mode(a.proj)
+    ops.set_bt_override(a.bt)
     tt.set_concurrency(not a.serial)
 
     torch.manual_seed(42)

@@ -34,18 +34,28 @@ constexpr int DG_PAD = 16;  // dGH rows are HP+16 floats apart (bank spread betw
 template <int HP, int G>
 constexpr int bwd_min_blocks() { return (HP * G <= 128) ? 3 : ((HP * G <= 256) ? 2 : 1); }
 
-template <int HP, int G, int BT, int TC, int NST>
-__global__ void __launch_bounds__(HP* G, bwd_min_blocks<HP, G>()) gru_bwd_kernel(BwdParams p) {
+// EXACT: H == HP at compile time (c2: 64, c3: 128): strides become immediates, the "real hidden unit" predicate
+// disappears.
+//
+// Per-step dependency chain.  Everything that does not depend on the carried dh is taken OFF the chain: the
+// saved r,z,n,q,h_{t-1},dy of step t-1 are fetched from the stage while step t's mat-vec runs, and folded into
+// four factors  A = (1-z)(1-n^2), Bz = (h_{t-1}-n) z (1-z), C = q r (1-r), r  -- so that once the carry arrives
+// the gate derivatives are  dh = dy + carry; dan = dh A; daz = dh Bz; dar = dan C; dq = dan r; cz = dh z :
+// three dependent FP32 ops between the reduce-scatter and the shared-memory exchange of dGH.
+template <int HP, int G, int BT, int TC, int NST, bool EXACT>
+__global__ void __launch_bounds__(HP* G, (EXACT || bwd_min_blocks<HP, G>() == 1) ? bwd_min_blocks<HP, G>() : bwd_min_blocks<HP, G>() - 1) gru_bwd_kernel(BwdParams p) {
   constexpr int KS = HP / G;
   constexpr int NOWN = (BT >= G) ? BT / G : 1;
   constexpr int HR = HP + DG_PAD;
+  constexpr bool DUAL = (HP * G <= 128);         // second accumulator set only where the register budget allows
   static_assert(KS % 4 == 0, "slice must be float4 granular");
   static_assert(G == 2 || G == 4, "lane groups of 2 or 4");
   static_assert(BT < G || BT % G == 0, "BT must be < G or a multiple of G");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int k = tid / G, ql = tid % G;
-  const int H = p.H, T = p.T;
+  const int H = EXACT ? HP : p.H;
+  const int T = p.T;
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
@@ -76,78 +86,127 @@ __global__ void __launch_bounds__(HP* G, bwd_min_blocks<HP, G>()) gru_bwd_kernel
         if (c & 1) wt[g][2 * i + (c >> 1)].y = v; else wt[g][2 * i + (c >> 1)].x = v;
       }
   for (int i = tid; i < 2 * BT * 3 * HR; i += HP * G) dgs[i] = 0.f;
-  // carry[o]: dL/dh_t[k] flowing in from step t+1 for the sequence this lane owns (b = o*G + ql, or b = ql)
+
+  bool act[NOWN];
+  int ob[NOWN];
+  // carry[o]: dL/dh_t[k] flowing in from step t+1 for the sequence this lane owns (b = o*G + ql, or b = ql).
+  // dy-last mode (discriminator head: the loss reads y[:, T-1] only): the (B,H) gradient IS the initial carry.
   float carry[NOWN];
+  const bool use_dy = !p.dy_last;
 #pragma unroll
-  for (int o = 0; o < NOWN; ++o) carry[o] = 0.f;
+  for (int o = 0; o < NOWN; ++o) {
+    ob[o] = (BT < G) ? ql % BT : o * G + ql;     // surplus lanes of a group repeat a sibling's (identical) work
+    act[o] = (EXACT && BT == 1) || ((EXACT || k < H) && (ob[o] < nb));
+    carry[o] = (p.dy_last && act[o]) ? p.dy[(size_t)(b0 + ob[o]) * H + k] : 0.f;
+  }
   pipe.start();
   __syncthreads();
 
+  const uint32_t dgs_addr = smem_u32(dgs);
+  const uint32_t h_step = 4u * (uint32_t)H, g_step = 12u * (uint32_t)H;
+  const uint32_t lane_k = 16u * (uint32_t)ql;
+
+  // factors of the step about to be processed + addresses of its rows
+  float fA[NOWN], fB[NOWN], fC[NOWN], fr[NOWN], fz[NOWN], fn[NOWN], fdy[NOWN];
+  uint32_t a_g[NOWN], a_q[NOWN], a_dy[NOWN], a_h[NOWN];
+
+  auto fetch = [&](bool first_t) __attribute__((always_inline)) {
+    // reads the rows a_* point at (step t), leaves the carry-independent factors in registers
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const float r = lds_f32(a_g[o]), z = lds_f32(a_g[o] + h_step), n = lds_f32(a_g[o] + 2u * h_step);
+      const float qv = lds_f32(a_q[o]);
+      float hp = lds_f32(a_h[o]);
+      hp = first_t ? 0.f : hp;                 // h_{-1} = 0 (the shifted stream never loads row -1)
+      float dyv = lds_f32(a_dy[o]);
+      dyv = use_dy ? dyv : 0.f;
+      const float omz = 1.f - z;
+      fA[o] = omz * fmaf(-n, n, 1.f);
+      fB[o] = (hp - n) * (z * omz);
+      fC[o] = qv * (r * (1.f - r));
+      fr[o] = r; fz[o] = z; fn[o] = n; fdy[o] = dyv;
+    }
+  };
+
   int par = 0;
+  float cz[NOWN];
+  auto step = [&](bool prefetch, bool next_first) __attribute__((always_inline)) {
+    const uint32_t dg = dgs_addr + (uint32_t)(par * BT * 3 * HR) * 4u;
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const float dh = fdy[o] + carry[o];
+      const float dan = dh * fA[o];
+      const float daz = dh * fB[o];
+      const float dar = dan * fC[o];
+      const float dqv = dan * fr[o];
+      cz[o] = dh * fz[o];
+      if (act[o]) {
+        const uint32_t d = dg + (uint32_t)((ob[o] * 3) * HR + k) * 4u;
+        sts_f32(d, dar); sts_f32(d + HR * 4u, daz); sts_f32(d + 2u * HR * 4u, dqv);
+        sts_f32(a_g[o], dar); sts_f32(a_g[o] + h_step, daz); sts_f32(a_g[o] + 2u * h_step, dan);
+        sts_f32(a_q[o], dqv);
+      }
+      a_g[o] -= g_step; a_q[o] -= h_step; a_dy[o] -= h_step; a_h[o] -= h_step;
+    }
+    // step t-1's operands are fetched now: their shared-memory latency and the factor arithmetic overlap
+    // the barrier and the mat-vec below
+    if (prefetch) fetch(next_first);
+  };
+
   for (int c = 0; c < pipe.NC; ++c) {
     pipe.acquire(c);
     const int s = c % NST;
     const int t0 = pipe.t0_of(c);
     const int tcn = pipe.tcn_of(c);
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const int b = act[o] ? ob[o] : 0;
+      const int kk = act[o] ? k : 0;
+      a_g[o] = pipe.row_addr(s, 0, b, tcn - 1) + 4u * (uint32_t)kk;
+      a_q[o] = pipe.row_addr(s, 1, b, tcn - 1) + 4u * (uint32_t)kk;
+      a_dy[o] = pipe.row_addr(s, 2, b, tcn - 1) + 4u * (uint32_t)kk;
+      a_h[o] = pipe.row_addr(s, 3, b, tcn - 1) + 4u * (uint32_t)kk;
+    }
+    fetch(t0 + tcn - 1 == 0);     // first step of the chunk: nothing to hide its fetch behind
     for (int tl = tcn - 1; tl >= 0; --tl) {
-      const int t = t0 + tl;
-      float* dg = dgs + par * BT * 3 * HR;
-      float cz[NOWN];
-      // ---- pointwise gate derivatives for hidden unit k of the owned sequences ----
-#pragma unroll
-      for (int o = 0; o < NOWN; ++o) {
-        const int b = (BT < G) ? ql : o * G + ql;
-        cz[o] = 0.f;
-        if (k < H && b < nb) {
-          float* gp = pipe.row(s, 0, b, tl);
-          float* qp = pipe.row(s, 1, b, tl);
-          const float r = gp[k], z = gp[H + k], n = gp[2 * H + k], qv = qp[k];
-          const float hp = (t > 0) ? pipe.row(s, 3, b, tl)[k] : 0.f;
-          float dyv;
-          if (p.dy_last) dyv = (t == T - 1) ? p.dy[(size_t)(b0 + b) * H + k] : 0.f;
-          else dyv = pipe.row(s, 2, b, tl)[k];
-          const float dh = dyv + carry[o];
-          const float dn = dh * (1.f - z);
-          const float dz = dh * (hp - n);
-          const float dan = dn * (1.f - n * n);
-          const float daz = dz * z * (1.f - z);
-          const float dar = dan * qv * r * (1.f - r);
-          const float dqv = dan * r;
-          cz[o] = dh * z;
-          gp[k] = dar; gp[H + k] = daz; gp[2 * H + k] = dan; qp[k] = dqv;
-          dg[(b * 3 + 0) * HR + k] = dar;
-          dg[(b * 3 + 1) * HR + k] = daz;
-          dg[(b * 3 + 2) * HR + k] = dqv;
-        }
-      }
-      if (tl == 0 && pipe.bulk) fence_async_smem();
+      // a_* point at step tl's rows; after the stores they move to step tl-1, which is prefetched unless this
+      // is the chunk's last step (tl == 0)
+      const bool last = (tl == 0);
+      step(!last, t0 + tl - 1 == 0);
+      if (last && pipe.bulk) fence_async_smem();
       __syncthreads();
-      // ---- carry_k = dh*z + sum_rows dGH[row] * W_hh[row][k] ----
-      // three independent packed accumulators per sequence (one per gate) keep the FFMA2 chains short
-      float2 acc2[BT][3];
+      // ---- mat-vec + reduce-scatter over the lane group: the owner of (k, b) receives the complete sum ----
+      const uint32_t dg = dgs_addr + (uint32_t)(par * BT * 3 * HR) * 4u;
+      float2 accA[BT][3], accB[BT][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) accA[b][g] = accB[b][g] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < KS / 4; ++i)
 #pragma unroll
         for (int g = 0; g < 3; ++g)
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
-            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 3 + g) * HR)[i * G + ql];
-            acc2[b][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(dv.x, dv.y), acc2[b][g]);
-            acc2[b][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(dv.z, dv.w), acc2[b][g]);
+            const float4 dv = lds_v4(dg + (uint32_t)((b * 3 + g) * HR) * 4u + (uint32_t)(i * G) * 16u + lane_k);
+            accA[b][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(dv.x, dv.y), accA[b][g]);
+            if constexpr (DUAL) accB[b][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(dv.z, dv.w), accB[b][g]);
+            else accA[b][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(dv.z, dv.w), accA[b][g]);
           }
       float acc[BT];
 #pragma unroll
-      for (int b = 0; b < BT; ++b)
-        acc[b] = (acc2[b][0].x + acc2[b][0].y) + (acc2[b][1].x + acc2[b][1].y) + (acc2[b][2].x + acc2[b][2].y);
-      // reduce-scatter over the lane group: the owner of (k, b) receives the complete sum
+      for (int b = 0; b < BT; ++b) {
+        const float u0 = (accA[b][0].x + accB[b][0].x) + (accA[b][0].y + accB[b][0].y);
+        const float u1 = (accA[b][1].x + accB[b][1].x) + (accA[b][1].y + accB[b][1].y);
+        const float u2 = (accA[b][2].x + accB[b][2].x) + (accA[b][2].y + accB[b][2].y);
+        acc[b] = (u0 + u1) + u2;
+      }
       if constexpr (BT < G) {
         float mine = 0.f;
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
           const float v = group_sum<G>(acc[b]);
-          mine = (ql == b) ? v : mine;
+          mine = (ql % BT == b) ? v : mine;
         }
         carry[0] = cz[0] + mine;
       } else if constexpr (G == 2) {
@@ -187,8 +246,10 @@ int launch_bwd(cudaStream_t st, const BwdParams& p) {
   constexpr int HR = HP + DG_PAD;
   size_t smem = ((2 * BT * 3 * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<4, BT, TC, NST>::stage_floats_for(widths) * 4;
-  auto kern = gru_bwd_kernel<HP, G, BT, TC, NST>;
-  TG_OPT_IN_SMEM(kern, "gru_bwd");
+  const bool exact = (p.H == HP);
+  auto kern = exact ? gru_bwd_kernel<HP, G, BT, TC, NST, true> : gru_bwd_kernel<HP, G, BT, TC, NST, false>;
+  if (exact) { TG_OPT_IN_SMEM((gru_bwd_kernel<HP, G, BT, TC, NST, true>), "gru_bwd"); }
+  else { TG_OPT_IN_SMEM((gru_bwd_kernel<HP, G, BT, TC, NST, false>), "gru_bwd"); }
   if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_bwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   dim3 grid((p.B + BT - 1) / BT), block(HP * G);
   kern<<<grid, block, smem, st>>>(p);

@@ -35,18 +35,22 @@ constexpr int HS_PAD = 16;  // h rows are HP+16 floats apart: the two sequences 
 template <int HP, int G, int BT>
 constexpr int fwd_min_blocks() { return (HP * G <= 128) ? 3 : ((HP * G <= 256) ? 2 : 1); }
 
-template <int HP, int G, int BT, int TC, int NST>
-__global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_kernel(FwdParams p) {
+// EXACT: H == HP is a compile-time fact (c2: 64, c3: 128) -- every stride in the hot loop becomes an immediate and
+// the "is this hidden unit real" predicate disappears.
+template <int HP, int G, int BT, int TC, int NST, bool EXACT>
+__global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() == 1) ? fwd_min_blocks<HP, G, BT>() : fwd_min_blocks<HP, G, BT>() - 1) gru_fwd_kernel(FwdParams p) {
   constexpr int KS = HP / G;                     // k values per lane
   constexpr int NOWN = (BT >= G) ? BT / G : 1;   // sequences a lane finishes per step
   constexpr int HR = HP + HS_PAD;
+  constexpr bool DUAL = (HP * G <= 128);         // second accumulator set only where the register budget allows
   static_assert(KS % 4 == 0, "k-slice must be float4 granular");
   static_assert(G == 2 || G == 4, "lane groups of 2 or 4");
   static_assert(BT < G || BT % G == 0, "BT must be < G or a multiple of G");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int j = tid / G, ql = tid % G;
-  const int H = p.H, T = p.T;
+  const int H = EXACT ? HP : p.H;
+  const int T = p.T;
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
@@ -93,120 +97,149 @@ __global__ void __launch_bounds__(HP* G, fwd_min_blocks<HP, G, BT>()) gru_fwd_ke
   int ob[NOWN];
 #pragma unroll
   for (int o = 0; o < NOWN; ++o) {
-    ob[o] = (BT < G) ? ql : o * G + ql;
-    act[o] = (j < H) && (ob[o] < nb);
+    // BT < G: the butterfly leaves every total in every lane, so lane q finishes sequence q % BT -- the surplus
+    // lanes repeat a sibling's work and stores (same values, same addresses) instead of idling behind a branch
+    ob[o] = (BT < G) ? ql % BT : o * G + ql;
+    // one sequence per CTA and H == HP: every lane is live -- a compile-time fact, so the stores need no branch
+    act[o] = (EXACT && BT == 1) || ((EXACT || j < H) && (ob[o] < nb));
   }
   const uint32_t gi_step = 12u * (uint32_t)H, h_step = 4u * (uint32_t)H;
   const uint32_t lane_k = 16u * (uint32_t)ql;          // this lane's first float4 of h
   const bool save = p.save != 0;
+  // the lane that owns sequence b seeds b's accumulators with the hidden biases of the r and z gates: the
+  // reduce-scatter then delivers (W_h h + b_h) and two additions leave the per-step dependency chain
+  float seed_r[BT], seed_z[BT];
+#pragma unroll
+  for (int b = 0; b < BT; ++b) {
+    const bool mine = (BT < G) ? (ql == b) : ((b % G) == ql);
+    seed_r[b] = mine ? bh[0] : 0.f;
+    seed_z[b] = mine ? bh[1] : 0.f;
+  }
 
   int cur = 0;
+  uint32_t a_gi[NOWN], a_q[NOWN], a_y[NOWN];
+
+  // One timestep.  Everything is computed unconditionally (inactive lanes work on row 0 of the stage and never
+  // store), so the body is branch-free: the warps do not pay for BSSY/BSYNC reconvergence every step.
+  auto step = [&]() __attribute__((always_inline)) {
+    const uint32_t hc = hs_addr + (uint32_t)(cur * BT * HR) * 4u;
+    const uint32_t hn = hs_addr + (uint32_t)((cur ^ 1) * BT * HR) * 4u;
+    // the input-projection values are fetched first so that their latency hides behind the mat-vec
+    float gr[NOWN], gz[NOWN], gn[NOWN];
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      gr[o] = lds_f32(a_gi[o]); gz[o] = lds_f32(a_gi[o] + h_step); gn[o] = lds_f32(a_gi[o] + 2u * h_step);
+    }
+    // two accumulator pairs per (sequence, gate): six independent FFMA2 chains per sequence keep the FMA pipe
+    // issuing every other cycle instead of waiting out the FFMA2 latency
+    float2 accA[BT][3], accB[BT][3];
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+      accA[b][0] = make_float2(seed_r[b], 0.f);
+      accA[b][1] = make_float2(seed_z[b], 0.f);
+      accA[b][2] = make_float2(0.f, 0.f);
+      accB[b][0] = accB[b][1] = accB[b][2] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < KS / 4; ++i) {
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u + lane_k);
+        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          accA[b][g] = __ffma2_rn(w[g][2 * i + 0], h01, accA[b][g]);
+          if constexpr (DUAL) accB[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, accB[b][g]);
+          else accA[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, accA[b][g]);
+        }
+      }
+    }
+    float acc[BT][3];
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) acc[b][g] = (accA[b][g].x + accB[b][g].x) + (accA[b][g].y + accB[b][g].y);
+    // ---- combine the G partial sums: own[o][g] = complete sum for sequence b = o*G + ql ----
+    float own[NOWN][3];
+    if constexpr (BT < G) {
+      // fewer sequences than lanes: butterfly, lane b finishes sequence b
+#pragma unroll
+      for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[b][g] = group_sum<G>(acc[b][g]);
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        own[0][g] = acc[0][g];
+#pragma unroll
+        for (int b = 1; b < BT; ++b) own[0][g] = (ql % BT == b) ? acc[b][g] : own[0][g];
+      }
+    } else if constexpr (G == 2) {
+#pragma unroll
+      for (int o = 0; o < NOWN; ++o)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const float send = ql ? acc[2 * o][g] : acc[2 * o + 1][g];
+          const float keep = ql ? acc[2 * o + 1][g] : acc[2 * o][g];
+          own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    } else {  // G == 4
+      const int hi = ql & 2, lo = ql & 1;
+#pragma unroll
+      for (int o = 0; o < NOWN; ++o)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const float s0 = hi ? acc[4 * o + 0][g] : acc[4 * o + 2][g];
+          const float k0 = hi ? acc[4 * o + 2][g] : acc[4 * o + 0][g];
+          const float s1 = hi ? acc[4 * o + 1][g] : acc[4 * o + 3][g];
+          const float k1 = hi ? acc[4 * o + 3][g] : acc[4 * o + 1][g];
+          const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
+          const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
+          const float send = lo ? a0 : a1;
+          const float keep = lo ? a1 : a0;
+          own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+        }
+    }
+    // ---- gates + state update for the sequences this lane owns ----
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      // BT < G: the butterfly leaves the same total (incl. the seeded bias) in every lane of the group
+      const float r = sigmoid_mufu(gr[o] + own[o][0]);
+      const float z = sigmoid_mufu(gz[o] + own[o][1]);
+      const float qv = own[o][2] + bh[2];
+      if (save && act[o]) { sts_f32(a_gi[o], r); sts_f32(a_gi[o] + h_step, z); sts_f32(a_q[o], qv); }
+      const float n = tanh_mufu(fmaf(r, qv, gn[o]));
+      const float h = fmaf(z, hprev[o] - n, n);
+      hprev[o] = h;
+      if (act[o]) {
+        sts_f32(hn + (uint32_t)(ob[o] * HR + j) * 4u, h);
+        sts_f32(a_y[o], h);
+        if (save) sts_f32(a_gi[o] + 2u * h_step, n);
+      }
+      a_gi[o] += gi_step; a_q[o] += h_step; a_y[o] += h_step;
+    }
+    cur ^= 1;
+  };
+
   for (int c = 0; c < pipe.NC; ++c) {
     pipe.acquire(c);
     const int s = c % NST;
     const int tcn = pipe.tcn_of(c);
-    uint32_t a_gi[NOWN], a_q[NOWN], a_y[NOWN];
 #pragma unroll
     for (int o = 0; o < NOWN; ++o) {
       const int b = act[o] ? ob[o] : 0;
-      a_gi[o] = pipe.row_addr(s, 0, b, 0) + 4u * (uint32_t)j;
-      a_q[o] = pipe.row_addr(s, 1, b, 0) + 4u * (uint32_t)j;
-      a_y[o] = pipe.row_addr(s, 2, b, 0) + 4u * (uint32_t)j;
+      const int jj = act[o] ? j : 0;
+      a_gi[o] = pipe.row_addr(s, 0, b, 0) + 4u * (uint32_t)jj;
+      a_q[o] = pipe.row_addr(s, 1, b, 0) + 4u * (uint32_t)jj;
+      a_y[o] = pipe.row_addr(s, 2, b, 0) + 4u * (uint32_t)jj;
     }
-    for (int tl = 0; tl < tcn; ++tl) {
-      const uint32_t hc = hs_addr + (uint32_t)(cur * BT * HR) * 4u;
-      const uint32_t hn = hs_addr + (uint32_t)((cur ^ 1) * BT * HR) * 4u;
-      // the input-projection values are fetched first so that their latency hides behind the mat-vec
-      float gr[NOWN], gz[NOWN], gn[NOWN];
-#pragma unroll
-      for (int o = 0; o < NOWN; ++o) {
-        gr[o] = gz[o] = gn[o] = 0.f;
-        if (act[o]) { gr[o] = lds_f32(a_gi[o]); gz[o] = lds_f32(a_gi[o] + h_step); gn[o] = lds_f32(a_gi[o] + 2u * h_step); }
-      }
-      float2 acc2[BT][3];
-#pragma unroll
-      for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < KS / 4; ++i) {
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u + lane_k);
-          const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            acc2[b][g] = __ffma2_rn(w[g][2 * i + 0], h01, acc2[b][g]);
-            acc2[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, acc2[b][g]);
-          }
-        }
-      }
-      float acc[BT][3];
-#pragma unroll
-      for (int b = 0; b < BT; ++b)
-#pragma unroll
-        for (int g = 0; g < 3; ++g) acc[b][g] = acc2[b][g].x + acc2[b][g].y;
-      // ---- combine the G partial sums: own[o][g] = complete sum for sequence b = o*G + ql ----
-      float own[NOWN][3];
-      if constexpr (BT < G) {
-        // fewer sequences than lanes: butterfly, lane b finishes sequence b
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-#pragma unroll
-          for (int g = 0; g < 3; ++g) acc[b][g] = group_sum<G>(acc[b][g]);
-#pragma unroll
-        for (int g = 0; g < 3; ++g) {
-          own[0][g] = acc[0][g];
-#pragma unroll
-          for (int b = 1; b < BT; ++b) own[0][g] = (ql == b) ? acc[b][g] : own[0][g];
-        }
-      } else if constexpr (G == 2) {
-#pragma unroll
-        for (int o = 0; o < NOWN; ++o)
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const float send = ql ? acc[2 * o][g] : acc[2 * o + 1][g];
-            const float keep = ql ? acc[2 * o + 1][g] : acc[2 * o][g];
-            own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-      } else {  // G == 4
-        const int hi = ql & 2, lo = ql & 1;
-#pragma unroll
-        for (int o = 0; o < NOWN; ++o)
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const float s0 = hi ? acc[4 * o + 0][g] : acc[4 * o + 2][g];
-            const float k0 = hi ? acc[4 * o + 2][g] : acc[4 * o + 0][g];
-            const float s1 = hi ? acc[4 * o + 1][g] : acc[4 * o + 3][g];
-            const float k1 = hi ? acc[4 * o + 3][g] : acc[4 * o + 1][g];
-            const float a0 = k0 + __shfl_xor_sync(0xffffffffu, s0, 2);
-            const float a1 = k1 + __shfl_xor_sync(0xffffffffu, s1, 2);
-            const float send = lo ? a0 : a1;
-            const float keep = lo ? a1 : a0;
-            own[o][g] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-          }
-      }
-      // ---- gates + state update for the sequences this lane owns ----
-#pragma unroll
-      for (int o = 0; o < NOWN; ++o) {
-        if (act[o]) {
-          const float r = sigmoid_mufu(gr[o] + own[o][0] + bh[0]);
-          const float z = sigmoid_mufu(gz[o] + own[o][1] + bh[1]);
-          const float qv = own[o][2] + bh[2];
-          const float n = tanh_mufu(fmaf(r, qv, gn[o]));
-          const float h = fmaf(z, hprev[o] - n, n);
-          hprev[o] = h;
-          sts_f32(hn + (uint32_t)(ob[o] * HR + j) * 4u, h);
-          sts_f32(a_y[o], h);
-          if (save) {
-            sts_f32(a_gi[o], r); sts_f32(a_gi[o] + h_step, z); sts_f32(a_gi[o] + 2u * h_step, n);
-            sts_f32(a_q[o], qv);
-          }
-        }
-        a_gi[o] += gi_step; a_q[o] += h_step; a_y[o] += h_step;
-      }
-      if (tl == tcn - 1 && pipe.bulk) fence_async_smem();
+    // the chunk's last step is peeled: only it needs the async-proxy fence before the stage is stored
+    for (int tl = 0; tl < tcn - 1; ++tl) {
+      step();
       __syncthreads();
-      cur ^= 1;
     }
+    step();
+    if (pipe.bulk) fence_async_smem();
+    __syncthreads();
     pipe.release(c);
   }
   pipe.drain();
@@ -218,8 +251,10 @@ int launch_fwd(cudaStream_t st, const FwdParams& p) {
   const int widths[3] = {3 * p.H, p.H, p.H};
   size_t smem = ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<3, BT, TC, NST>::stage_floats_for(widths) * 4;
-  auto kern = gru_fwd_kernel<HP, G, BT, TC, NST>;
-  TG_OPT_IN_SMEM(kern, "gru_fwd");
+  const bool exact = (p.H == HP);
+  auto kern = exact ? gru_fwd_kernel<HP, G, BT, TC, NST, true> : gru_fwd_kernel<HP, G, BT, TC, NST, false>;
+  if (exact) { TG_OPT_IN_SMEM((gru_fwd_kernel<HP, G, BT, TC, NST, true>), "gru_fwd"); }
+  else { TG_OPT_IN_SMEM((gru_fwd_kernel<HP, G, BT, TC, NST, false>), "gru_fwd"); }
   if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_fwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   dim3 grid((p.B + BT - 1) / BT), block(HP * G);
   kern<<<grid, block, smem, st>>>(p);
