@@ -6,6 +6,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 
 static thread_local char g_err[512] = "";
@@ -89,6 +90,34 @@ int tg_max_optin_smem() {
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&x, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || x <= 0)
       return 227 * 1024;
+    v.store(x);
+  }
+  return x;
+}
+
+// Shared-memory budget of the persistent tensor-core GEMM CTAs.  Default: the whole opt-in maximum (one CTA owns
+// the SM).  A smaller budget (TIMEGAN_B200_GEMM_SMEM_KB) leaves room for CTAs of the recurrent kernels issued on
+// another stream to be co-resident, at the price of shallower TMA rings.
+int tg_gemm_smem_budget() {
+  static std::atomic<int> v{0};
+  int x = v.load();
+  if (x == 0) {
+    x = tg_max_optin_smem();
+    const char* e = getenv("TIMEGAN_B200_GEMM_SMEM_KB");
+    if (e && atoi(e) >= 48 && atoi(e) * 1024 < x) x = atoi(e) * 1024;
+    v.store(x);
+  }
+  return x;
+}
+
+// long chunks (16 timesteps per ring stage instead of 8) for the one-sequence-per-CTA recurrent kernels;
+// TIMEGAN_B200_LONG_CHUNKS=0 switches back
+int tg_long_chunks() {
+  static std::atomic<int> v{-1};
+  int x = v.load();
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_LONG_CHUNKS");
+    x = (e && atoi(e) == 0) ? 0 : 1;
     v.store(x);
   }
   return x;

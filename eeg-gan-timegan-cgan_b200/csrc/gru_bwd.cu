@@ -259,6 +259,9 @@ int launch_bwd(cudaStream_t st, const BwdParams& p) {
 template <int HP, int G>
 int dispatch_bt(cudaStream_t st, const BwdParams& p, int bt) {
   constexpr int TC = (HP >= 128) ? 4 : 8, NST = 3;
+  // one sequence per CTA (the co-resident, latency-bound regime): 16-step chunks halve the per-chunk cost of the
+  // bulk-copy ring (thread 0 issues the stores/loads while the other warps wait at the next barrier)
+  if (HP <= 64 && bt == 1 && tg_long_chunks()) return launch_bwd<HP, G, 1, 2 * TC, NST>(st, p);
   switch (bt) {
     case 1: return launch_bwd<HP, G, 1, TC, NST>(st, p);
     case 2: return launch_bwd<HP, G, 2, TC, NST>(st, p);

@@ -57,6 +57,8 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
                          float* dW_ih, float* dW_hh, float* db_ih, float* db_hh, int B, int T, int I, int H,
                          int accumulate, float* ws, size_t ws_bytes, int passes);
 int tg_max_optin_smem();
+int tg_gemm_smem_budget();
+int tg_long_chunks();
 
 // column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)
 size_t tg_colsum_ws_bytes(int N);

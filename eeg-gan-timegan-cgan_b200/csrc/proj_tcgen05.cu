@@ -258,7 +258,7 @@ int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, in
   for (; n_tiles <= 16; ++n_tiles) {
     NT = ((n_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
     w_total = ((copies * KB * NT * 128) + 1023) / 1024 * 1024;
-    nstage = (225 * 1024 - w_total - TAIL_BYTES) / stage_bytes;
+    nstage = (tg_gemm_smem_budget() - 2048 - w_total - TAIL_BYTES) / stage_bytes;
     if (nstage >= 3) break;
   }
   if (nstage > 8) nstage = 8;

@@ -315,7 +315,7 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
   int R = 32, nstage = 0;
   for (; R >= 8; R >>= 1) {
     const int stage_bytes = (GCH + ACH) * R * 128;
-    nstage = (tg_max_optin_smem() - WL_TAIL - 4 * R * 128) / stage_bytes - (passes == 3 ? 2 : 0);
+    nstage = (tg_gemm_smem_budget() - WL_TAIL - 4 * R * 128) / stage_bytes - (passes == 3 ? 2 : 0);
     if (nstage >= 4) break;
   }
   if (R < 8 || nstage < 3) { tg_set_error("wgrad_gru: tile does not fit shared memory"); return TG_ERR_UNSUPPORTED; }

@@ -278,7 +278,7 @@ int tg_wgrad_tc_impl(cudaStream_t st, const float* dG, int ldg, const float* A, 
   int R = 64, nstage = 0;
   for (; R >= 8; R >>= 1) {
     const int stage_bytes = copies * (NCH + KCH) * R * 128;
-    nstage = (tg_max_optin_smem() - WG_TAIL - 4 * R * 128) / stage_bytes;
+    nstage = (tg_gemm_smem_budget() - WG_TAIL - 4 * R * 128) / stage_bytes;
     if (nstage >= 3) break;
   }
   if (R < 8 || nstage < 3) { tg_set_error("wgrad_tc: tile does not fit shared memory"); return TG_ERR_UNSUPPORTED; }
