@@ -56,12 +56,12 @@ __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
+        : "r"(addr), "r"(parity), "r"(0x989680u)   // suspend-time hint: the warp sleeps in hardware until the
+        : "memory");                                // phase completes instead of spinning away issue slots
     if (ok) return;
     if (clock64() - t0 > 4000000000LL) {
       printf("timegan_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);

@@ -172,6 +172,8 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
 #pragma unroll
     for (int c = 0; c < WL_MAXCH / 2; ++c) colsum[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int NCHK = GCH + ACH;
+    // (first row of the stage) mod T, kept incrementally: a 64-bit modulo per row costs ~100 instructions
+    int rem0 = (int)(row_begin % p.T);
     for (int it = 0; it < steps; ++it) {
       const int s = it % NS;
       mbar_wait_bounded(&full[s], (uint32_t)((it / NS) & 1));
@@ -181,9 +183,10 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       }
       unsigned char* base = smem + (size_t)s * stage_bytes;
       unsigned char* lo = lo_base + (size_t)(it & 1) * stage_bytes;
-      const long long r0 = row_begin + (long long)it * R;
       for (int r = rsub; r < R; r += 16) {
-        const bool boundary = ((r0 + r) % p.T) == 0;
+        int rr = rem0 + r;
+        while (rr >= p.T) rr -= p.T;
+        const bool boundary = rr == 0;
         const size_t off = (size_t)r * 128 + (size_t)u * 16;
         // three chunks per batch: the loads are issued together (the compiler cannot reorder them across the
         // in-place stores by itself), then column sums / h_{-1} zeroing / TF32 split, then the stores
@@ -215,6 +218,8 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       }
       fence_async_smem();
       mbar_arrive(&ready[s]);
+      rem0 += R;
+      while (rem0 >= p.T) rem0 -= p.T;
     }
     // per-CTA column-sum partial (bias gradients)
     mbar_wait_bounded(acc_full, 0);
