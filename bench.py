@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dp-graph", action="store_true", help="experimental: capture the NCCL all-reduces too (N > 1)")
     ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
+    ap.add_argument("--wgrad-ctas", type=int, default=-1,
+                    help="SMs given to the side-stream weight-gradient kernels (0 = in line; -1 = package default)")
     ap.add_argument("--bt", type=int, default=0, choices=[0, 1, 2, 4],
                     help="sequences per CTA in the recurrent kernels (0 = the library's heuristic)")
     return ap.parse_args()
@@ -207,6 +209,8 @@ def run_ours(a):
         tdist.init(backend="nccl", device=dev)
     ops.set_proj_mode(a.proj)
     ops.set_bt_override(a.bt)
+    if a.wgrad_ctas >= 0:
+        ops.set_wgrad_overlap(a.wgrad_ctas)
     tt.set_concurrency(not a.serial)
 
     torch.manual_seed(42)

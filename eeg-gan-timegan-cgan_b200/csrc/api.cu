@@ -123,6 +123,9 @@ int tg_long_chunks() {
   return x;
 }
 
+static std::atomic<int> g_wgrad_cta_cap{0};
+int tg_wgrad_cta_cap() { return g_wgrad_cta_cap.load(std::memory_order_relaxed); }
+
 size_t tg_sumsq_ws_bytes(int n, const long long* sizes);
 
 extern "C" {
@@ -130,6 +133,11 @@ extern "C" {
 int tg_version(void) { return TG_ABI_VERSION; }
 const char* tg_last_error(void) { return g_err; }
 int tg_device_sm_count(void) { return tg_num_sms(); }
+int tg_set_option(const char* key, int value) {
+  if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
+  tg_set_error("set_option: unknown key '%s'", key ? key : "(null)");
+  return TG_ERR_ARG;
+}
 
 long long tg_launch_count(void) { return g_launches.load(); }
 int tg_prof_kinds(void) { return K_COUNT; }

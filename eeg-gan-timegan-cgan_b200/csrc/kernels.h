@@ -59,6 +59,7 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
 int tg_max_optin_smem();
 int tg_gemm_smem_budget();
 int tg_long_chunks();
+int tg_wgrad_cta_cap();
 
 // column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)
 size_t tg_colsum_ws_bytes(int N);

@@ -281,6 +281,8 @@ __global__ void wgrad_layer_reduce_kernel(const float* __restrict__ ws, int spli
 
 int wl_splits(int M) {
   int s = tg_num_sms();
+  const int cap = tg_wgrad_cta_cap();   // > 0: leave the other SMs to kernels running on other streams
+  if (cap > 0 && cap < s) s = cap;
   const int max_s = (M + 255) / 256;
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;

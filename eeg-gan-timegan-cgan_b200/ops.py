@@ -54,6 +54,53 @@ def _flags(base: int = 0) -> int:
     return base | (_BT_OVERRIDE << 8)
 
 
+# Weight gradients off the critical path: nothing downstream of BPTT needs dW until clip + Adam, so the fused
+# weight-gradient kernel of layer l can run while layer l-1's BPTT is already going -- on a side stream and on a
+# CAPPED number of SMs (it is a one-CTA-per-SM persistent kernel that owns the whole shared memory of its SM, so
+# an uncapped launch would simply push the recurrent kernel out).  0 = in line on the calling stream.
+_WGRAD_CTAS = 0
+_WGRAD_STREAMS = {}
+
+
+def set_wgrad_overlap(n_ctas: int):
+    """n_ctas > 0: run the per-layer weight-gradient kernels on a side stream using at most n_ctas SMs."""
+    global _WGRAD_CTAS
+    _WGRAD_CTAS = max(0, int(n_ctas))
+    check(lib.tg_set_option(b"wgrad_ctas", _WGRAD_CTAS), "tg_set_option")
+
+
+class _WgradSide:
+    """Per stack-backward helper: issue(fn, *keep) runs fn on the side stream after everything issued so far on
+    the calling stream; join() makes the calling stream wait for it.  Tensors the side stream reads are kept
+    referenced until join(), so the caching allocator cannot hand their blocks to later main-stream allocations."""
+
+    def __init__(self, device):
+        self.on = _WGRAD_CTAS > 0
+        self.keep = []
+        if self.on:
+            self.main = torch.cuda.current_stream(device)
+            key = (str(device), self.main.cuda_stream)
+            if key not in _WGRAD_STREAMS:
+                _WGRAD_STREAMS[key] = torch.cuda.Stream(device=device)
+            self.side = _WGRAD_STREAMS[key]
+            self.used = False
+
+    def issue(self, fn, *keep):
+        if not self.on:
+            fn()
+            return
+        self.keep.extend(keep)
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            fn()
+        self.used = True
+
+    def join(self):
+        if self.on and self.used:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
 class LayerSave:
     """Activations one layer keeps for its backward pass (all (B,T,*) fp32, contiguous)."""
     __slots__ = ("inp", "rzn", "q", "y")
@@ -194,6 +241,7 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
     d = dy.contiguous()
     last_only = dy_last
     dx = None
+    side = _WgradSide(dev)
     for l in reversed(range(L)):
         sv = saves[l]
         w_ih, w_hh, _, _ = _layer_weights(weights, l)
@@ -206,15 +254,17 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
                              B, T, H, _flags(_lib.GRU_DY_LAST if last_only else 0), ptr(w_hh_t)), "tg_gru_bwd")
         last_only = False
         dgi2 = dgi.view(B * T, 3 * H)
-        if need_dw:
-            g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
-            wgrad_gru(dgi, dq, sv.inp.reshape(B * T, I), sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
-        if l > 0 or need_dx:
+        if l > 0 or need_dx:          # the critical path first: dX feeds the next layer's BPTT
             dx = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             dgrad(dgi2, w_ih, dx.view(B * T, I))
             d = dx
             if masks is not None and l > 0:
                 d = dx * masks[l - 1]
+        if need_dw:
+            g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
+            x2 = sv.inp.reshape(B * T, I)
+            side.issue(lambda: wgrad_gru(dgi, dq, x2, sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate), dgi, dq, x2)
+    side.join()
     return (dx if need_dx else None), grads
 
 
@@ -262,6 +312,7 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
     dev = hbar_last.device
     hb, hdb = hbar_last.contiguous(), hdbar_last.contiguous()
     last_only = True
+    side = _WgradSide(dev)
     for l in reversed(range(L)):
         sv, ts = saves[l], tsaves[l]
         w_ih, w_hh, _, _ = _layer_weights(weights, l)
@@ -279,17 +330,21 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
         g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
         gib2, gidb2 = gib.view(B * T, 3 * H), gidb.view(B * T, 3 * H)
         y2, yd2 = sv.y.view(B * T, H), ts.ydot.view(B * T, H)
-        # primal path
-        wgrad_gru(gib, qb, sv.inp.reshape(B * T, I), sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
-        # tangent path (no bias terms in the tangent)
-        wgrad_gru(gidb, qdb, ts.xdot.reshape(B * T, I), ts.ydot, g_wih, g_whh, None, None, True)
-        if l > 0:
+        if l > 0:                     # the critical path first
             hb = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             hdb = torch.empty(B, T, I, dtype=torch.float32, device=dev)
             dgrad(gib2, w_ih, hb.view(B * T, I))
             dgrad(gidb2, w_ih, hdb.view(B * T, I))
             if masks is not None:
                 hb, hdb = hb * masks[l - 1], hdb * masks[l - 1]
+
+        def _wg(gib=gib, qb=qb, gidb=gidb, qdb=qdb, sv=sv, ts=ts, g_wih=g_wih, g_whh=g_whh, g_bih=g_bih,
+                g_bhh=g_bhh, I=I):
+            # primal path, then tangent path (no bias terms in the tangent)
+            wgrad_gru(gib, qb, sv.inp.reshape(B * T, I), sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
+            wgrad_gru(gidb, qdb, ts.xdot.reshape(B * T, I), ts.ydot, g_wih, g_whh, None, None, True)
+        side.issue(_wg, gib, qb, gidb, qdb)
+    side.join()
 
 
 def alloc_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 5
+#define TG_ABI_VERSION 6
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -45,6 +45,10 @@ extern "C" {
 int tg_version(void);
 const char* tg_last_error(void);
 int tg_device_sm_count(void);
+/* Process-wide tuning knobs.  "wgrad_ctas" = N > 0: the fused weight-gradient kernel (tg_wgrad_gru) uses at most N
+ * CTAs (one per SM), leaving the other SMs to recurrent kernels issued on another stream; 0 = one CTA per SM.
+ * Must not change between tg_wgrad_gru_workspace_bytes and the tg_wgrad_gru call that uses the workspace. */
+int tg_set_option(const char* key, int value);
 
 /* ---- launch accounting and per-family device timing (measurement only; used by bench.py) -------------------
  * tg_launch_count: kernels launched by this library since load.  With tg_prof_enable(1) every call below is
