@@ -334,6 +334,15 @@ def run_ours(a):
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
+    # DRAM traffic of the dominant family's representative launch, from the committed `ncu --set full` capture
+    try:
+        tr = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())
+        if workload_name(a).startswith("c2") and tr.get("workload") == "c2":
+            traffic_tab = tr["kernels"]
+        else:
+            traffic_tab = {}
+    except Exception:
+        traffic_tab = {}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     total_dev_ms = sum(v["ms"] for v in prof.values()) or 1.0
@@ -361,7 +370,11 @@ def run_ours(a):
         "host_issue_ms_per_step": round(host_issue_ms / a.steps, 3),
         "clocks": clk,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(ach_gbs / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                     "frac": round(ach_gbs / hbm_peak, 4),
+                     "traffic": (traffic_tab.get(dom) or {}).get("dram_bytes_per_launch"),
+                     "traffic_note": (traffic_tab.get(dom) or {}).get("note"),
+                     "algorithmic_bytes_per_launch": round(d["bytes"] / max(d["calls"], 1)),
+                     "peak_source": peak_src,
                      "avg_launch_ms": round(d["ms"] / max(d["calls"], 1), 4), "launches": d["calls"],
                      "share_of_device_time": round(d["ms"] / total_dev_ms, 4),
                      "timing": "CUDA-event pair around every C-ABI call of the family, summed over eagerly issued, "

@@ -27,6 +27,17 @@ def test_library_exports_every_declared_symbol():
     assert _lib.ABI_VERSION == int(re.search(r"#define TG_ABI_VERSION (\d+)", (ROOT / "include" / "timegan_b200.h").read_text()).group(1))
 
 
+def test_set_option_knobs():
+    from timegan_b200 import _lib
+    before = _lib.lib.tg_wgrad_gru_workspace_bytes(256, 768, 64, 64)
+    assert _lib.lib.tg_set_option(b"wgrad_ctas", 37) == 0
+    capped = _lib.lib.tg_wgrad_gru_workspace_bytes(256, 768, 64, 64)
+    assert _lib.lib.tg_set_option(b"wgrad_ctas", 0) == 0
+    assert _lib.lib.tg_wgrad_gru_workspace_bytes(256, 768, 64, 64) == before
+    assert 0 < capped <= before                      # one partial per CTA: fewer CTAs, smaller workspace
+    assert _lib.lib.tg_set_option(b"no_such_knob", 1) < 0 and "unknown key" in _lib.last_error()
+
+
 def test_argument_errors_are_reported_not_crashed():
     from timegan_b200 import _lib
     rc = _lib.lib.tg_gru_fwd(None, None, None, None, None, None, 1, 1, 1, 0)
