@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(HP* G, (EXACT || bwd_min_blocks<HP, G>() == 1)
 
   int par = 0;
   float cz[NOWN];
-  auto step = [&](bool prefetch, bool next_first) __attribute__((always_inline)) {
+  auto step = [&]() __attribute__((always_inline)) {
     const uint32_t dg = dgs_addr + (uint32_t)(par * BT * 3 * HR) * 4u;
 #pragma unroll
     for (int o = 0; o < NOWN; ++o) {
@@ -148,9 +148,6 @@ __global__ void __launch_bounds__(HP* G, (EXACT || bwd_min_blocks<HP, G>() == 1)
       }
       a_g[o] -= g_step; a_q[o] -= h_step; a_dy[o] -= h_step; a_h[o] -= h_step;
     }
-    // step t-1's operands are fetched now: their shared-memory latency and the factor arithmetic overlap
-    // the barrier and the mat-vec below
-    if (prefetch) fetch(next_first);
   };
 
   for (int c = 0; c < pipe.NC; ++c) {
@@ -172,9 +169,12 @@ __global__ void __launch_bounds__(HP* G, (EXACT || bwd_min_blocks<HP, G>() == 1)
       // a_* point at step tl's rows; after the stores they move to step tl-1, which is prefetched unless this
       // is the chunk's last step (tl == 0)
       const bool last = (tl == 0);
-      step(!last, t0 + tl - 1 == 0);
+      step();
       if (last && pipe.bulk) fence_async_smem();
       __syncthreads();
+      // step t-1's operands are fetched HERE, in the same basic block as the mat-vec: their shared-memory latency
+      // and the factor arithmetic interleave with the FFMA2 stream instead of sitting in front of the barrier
+      if (!last) fetch(t0 + tl - 1 == 0);
       // ---- mat-vec + reduce-scatter over the lane group: the owner of (k, b) receives the complete sum ----
       const uint32_t dg = dgs_addr + (uint32_t)(par * BT * 3 * HR) * 4u;
       float2 accA[BT][3], accB[BT][3];

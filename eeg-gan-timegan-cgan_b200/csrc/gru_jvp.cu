@@ -46,7 +46,7 @@ __device__ __forceinline__ void jvp_reduce_scatter(float (&acc)[BT][NV], float (
 #pragma unroll
       for (int b = 0; b < BT; ++b) {
         const float t = group_sum<G>(acc[b][v]);
-        mine = (ql == b) ? t : mine;
+        mine = (ql % BT == b) ? t : mine;
       }
       own[0][v] = mine;
     }
@@ -78,7 +78,14 @@ __device__ __forceinline__ void jvp_reduce_scatter(float (&acc)[BT][NV], float (
   }
 }
 
-template <int HP, int G, int BT, int TC, int NST>
+// The tangent recurrence is LINEAR in hdot (the gates are those of the saved primal pass), so once the lane group's
+// W_hh hdot_{t-1} sums arrive only a handful of dependent FP32 ops remain:
+//     a_r = gid_r + s_r;  rdot = c1 a_r;  a_n = gid_n + rdot q + r s_n;  ndot = c3 a_n;
+//     a_z = gid_z + s_z;  zdot = c2 a_z;  hdot = (1-z) ndot + z hdot_{t-1} + zdot (h_{t-1} - n)
+// with c1 = r(1-r), c2 = z(1-z), c3 = 1-n^2.  The saved operands are fetched (and the coefficients formed) in the
+// same basic block as the mat-vec, so they hide behind its FFMA2 stream; the body is branch-free and EXACT
+// (H == HP) turns the strides into immediates.
+template <int HP, int G, int BT, int TC, int NST, bool EXACT>
 __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_fwd_kernel(JfParams p) {
   constexpr int KS = HP / G;
   constexpr int NOWN = (BT >= G) ? BT / G : 1;
@@ -86,7 +93,8 @@ __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_fwd_ke
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int j = tid / G, ql = tid % G;
-  const int H = p.H, T = p.T;
+  const int H = EXACT ? HP : p.H;
+  const int T = p.T;
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
@@ -119,69 +127,114 @@ __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_fwd_ke
       }
   for (int i = tid; i < 2 * BT * HR; i += HP * G) hs[i] = 0.f;
   float hdprev[NOWN];
+  bool act[NOWN];
+  int ob[NOWN];
 #pragma unroll
-  for (int o = 0; o < NOWN; ++o) hdprev[o] = 0.f;
+  for (int o = 0; o < NOWN; ++o) {
+    hdprev[o] = 0.f;
+    ob[o] = (BT < G) ? ql % BT : o * G + ql;     // surplus lanes of a group repeat a sibling's (identical) work
+    act[o] = (EXACT && BT == 1) || ((EXACT || j < H) && (ob[o] < nb));
+  }
   pipe.start();
   __syncthreads();
 
+  const uint32_t hs_addr = smem_u32(hs);
+  const uint32_t h_step = 4u * (uint32_t)H, g_step = 12u * (uint32_t)H;
+  const uint32_t lane_k = 16u * (uint32_t)ql;
+  uint32_t a_g[NOWN], a_s[NOWN], a_q[NOWN], a_h[NOWN], a_qd[NOWN], a_yd[NOWN];
+  float gr[NOWN], gz[NOWN], gn[NOWN], c1[NOWN], c2[NOWN], c3[NOWN], fr[NOWN], fz[NOWN], fq[NOWN], fomz[NOWN], fhmn[NOWN];
+
+  auto fetch = [&](bool first_t) __attribute__((always_inline)) {
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      gr[o] = lds_f32(a_g[o]); gz[o] = lds_f32(a_g[o] + h_step); gn[o] = lds_f32(a_g[o] + 2u * h_step);
+      const float r = lds_f32(a_s[o]), z = lds_f32(a_s[o] + h_step), n = lds_f32(a_s[o] + 2u * h_step);
+      fq[o] = lds_f32(a_q[o]);
+      float hp = lds_f32(a_h[o]);
+      hp = first_t ? 0.f : hp;                 // h_{-1} = 0 (the shifted stream never loads row -1)
+      fr[o] = r; fz[o] = z;
+      c1[o] = r * (1.f - r);
+      fomz[o] = 1.f - z;
+      c2[o] = z * fomz[o];
+      c3[o] = fmaf(-n, n, 1.f);
+      fhmn[o] = hp - n;
+    }
+  };
+
   int cur = 0;
+  auto step = [&](bool first_t) __attribute__((always_inline)) {
+    const uint32_t hc = hs_addr + (uint32_t)(cur * BT * HR) * 4u;
+    const uint32_t hn = hs_addr + (uint32_t)((cur ^ 1) * BT * HR) * 4u;
+    fetch(first_t);      // same basic block as the mat-vec: the loads and the coefficient math hide behind it
+    float2 accA[BT][3], accB[BT][3];
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) accA[b][g] = accB[b][g] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < KS / 4; ++i)
+#pragma unroll
+      for (int b = 0; b < BT; ++b) {
+        const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u + lane_k);
+        const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          accA[b][g] = __ffma2_rn(w[g][2 * i + 0], h01, accA[b][g]);
+          if constexpr (HP * G <= 128) accB[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, accB[b][g]);
+          else accA[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, accA[b][g]);
+        }
+      }
+    float acc[BT][3], own[NOWN][3];
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+      for (int g = 0; g < 3; ++g) acc[b][g] = (accA[b][g].x + accB[b][g].x) + (accA[b][g].y + accB[b][g].y);
+    jvp_reduce_scatter<G, BT, 3>(acc, own, ql);
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const float qd = own[o][2];
+      const float a_r = gr[o] + own[o][0];
+      const float a_z = gz[o] + own[o][1];
+      const float rdot = c1[o] * a_r;
+      const float zdot = c2[o] * a_z;
+      const float a_n = fmaf(fr[o], qd, fmaf(rdot, fq[o], gn[o]));
+      const float ndot = c3[o] * a_n;
+      const float hd = fmaf(zdot, fhmn[o], fmaf(fz[o], hdprev[o], fomz[o] * ndot));
+      hdprev[o] = hd;
+      if (act[o]) {
+        sts_f32(hn + (uint32_t)(ob[o] * HR + j) * 4u, hd);
+        sts_f32(a_yd[o], hd);
+        sts_f32(a_qd[o], qd);
+        sts_f32(a_g[o], a_r); sts_f32(a_g[o] + h_step, a_z); sts_f32(a_g[o] + 2u * h_step, a_n);
+      }
+      a_g[o] += g_step; a_s[o] += g_step; a_q[o] += h_step; a_h[o] += h_step; a_qd[o] += h_step; a_yd[o] += h_step;
+    }
+    cur ^= 1;
+  };
+
   for (int c = 0; c < pipe.NC; ++c) {
     pipe.acquire(c);
     const int s = c % NST;
     const int t0 = pipe.t0_of(c);
     const int tcn = pipe.tcn_of(c);
-    for (int tl = 0; tl < tcn; ++tl) {
-      const float* hc = hs + cur * BT * HR;
-      float* hn = hs + (cur ^ 1) * BT * HR;
-      float2 acc2[BT][3];
 #pragma unroll
-      for (int b = 0; b < BT; ++b) acc2[b][0] = acc2[b][1] = acc2[b][2] = make_float2(0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < KS / 4; ++i)
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          const float4 hv = reinterpret_cast<const float4*>(hc + b * HR)[i * G + ql];
-          const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            acc2[b][g] = __ffma2_rn(w[g][2 * i + 0], h01, acc2[b][g]);
-            acc2[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, acc2[b][g]);
-          }
-        }
-      float acc[BT][3], own[NOWN][3];
-#pragma unroll
-      for (int b = 0; b < BT; ++b)
-#pragma unroll
-        for (int g = 0; g < 3; ++g) acc[b][g] = acc2[b][g].x + acc2[b][g].y;
-      jvp_reduce_scatter<G, BT, 3>(acc, own, ql);
-#pragma unroll
-      for (int o = 0; o < NOWN; ++o) {
-        const int b = (BT < G) ? ql : o * G + ql;
-        if (j < H && b < nb) {
-          float* gp = pipe.row(s, 0, b, tl);
-          const float* sp = pipe.row(s, 1, b, tl);
-          const float r = sp[j], z = sp[H + j], n = sp[2 * H + j];
-          const float qv = pipe.row(s, 2, b, tl)[j];
-          const float hp = (t0 + tl > 0) ? pipe.row(s, 3, b, tl)[j] : 0.f;
-          const float a_r = gp[j] + own[o][0];
-          const float a_z = gp[H + j] + own[o][1];
-          const float qd = own[o][2];
-          const float rdot = r * (1.f - r) * a_r;
-          const float zdot = z * (1.f - z) * a_z;
-          const float a_n = gp[2 * H + j] + rdot * qv + r * qd;
-          const float ndot = (1.f - n * n) * a_n;
-          const float hd = (1.f - z) * ndot + z * hdprev[o] + zdot * (hp - n);
-          hdprev[o] = hd;
-          hn[b * HR + j] = hd;
-          gp[j] = a_r; gp[H + j] = a_z; gp[2 * H + j] = a_n;
-          pipe.row(s, 4, b, tl)[j] = qd;
-          pipe.row(s, 5, b, tl)[j] = hd;
-        }
-      }
-      if (tl == tcn - 1 && pipe.bulk) fence_async_smem();
-      __syncthreads();
-      cur ^= 1;
+    for (int o = 0; o < NOWN; ++o) {
+      const int b = act[o] ? ob[o] : 0;
+      const int jj = act[o] ? j : 0;
+      a_g[o] = pipe.row_addr(s, 0, b, 0) + 4u * (uint32_t)jj;
+      a_s[o] = pipe.row_addr(s, 1, b, 0) + 4u * (uint32_t)jj;
+      a_q[o] = pipe.row_addr(s, 2, b, 0) + 4u * (uint32_t)jj;
+      a_h[o] = pipe.row_addr(s, 3, b, 0) + 4u * (uint32_t)jj;
+      a_qd[o] = pipe.row_addr(s, 4, b, 0) + 4u * (uint32_t)jj;
+      a_yd[o] = pipe.row_addr(s, 5, b, 0) + 4u * (uint32_t)jj;
     }
+    for (int tl = 0; tl < tcn - 1; ++tl) {
+      step(t0 + tl == 0);
+      __syncthreads();
+    }
+    step(t0 + tcn - 1 == 0);
+    if (pipe.bulk) fence_async_smem();
+    __syncthreads();
     pipe.release(c);
   }
   pipe.drain();
@@ -207,7 +260,13 @@ struct JbParams {
   int bulk;
 };
 
-template <int HP, int G, int BT, int TC, int NST>
+// Every output of a step is LINEAR in the two incoming adjoints hb = hbar_t + carry_h, hdb = hdbar_t + carry_hd,
+// with coefficients that only depend on saved activations:  out = alpha hb + beta hdb.  The coefficient pairs of
+// step t-1 are formed in the same basic block as step t's mat-vecs (operands fetched from the stage right after
+// the barrier), so the chain between the
+// reduce-scatter and the shared-memory exchange is  FADD -> FMUL -> FFMA.  (Derivation: oracle/gru_math.py
+// gru_layer_jvp_bwd; K1 = (1-n^2)(1-z), K2 = (1-n^2)(-zdot - 2 n a_n (1-z)).)
+template <int HP, int G, int BT, int TC, int NST, bool EXACT>
 __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_bwd_kernel(JbParams p) {
   constexpr int KS = HP / G;
   constexpr int NOWN = (BT >= G) ? BT / G : 1;
@@ -215,7 +274,8 @@ __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_bwd_ke
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int k = tid / G, ql = tid % G;
-  const int H = p.H, T = p.T;
+  const int H = EXACT ? HP : p.H;
+  const int T = p.T;
   const int b0 = blockIdx.x * BT;
   const int nb = min(BT, p.B - b0);
 
@@ -250,86 +310,118 @@ __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_bwd_ke
         if (c & 1) wt[g][2 * i + (c >> 1)].y = v; else wt[g][2 * i + (c >> 1)].x = v;
       }
   for (int i = tid; i < 2 * BT * 6 * HR; i += HP * G) dgs[i] = 0.f;
+  // carried adjoints; last-only mode (R1: the head reads y[:, T-1] / ydot[:, T-1]): the (B,H) adjoints ARE the
+  // initial carries and no per-step adjoint stream exists
   float ch[NOWN], chd[NOWN];
+  bool act[NOWN];
+  int ob[NOWN];
+  const bool use_bar = !p.last_only;
 #pragma unroll
-  for (int o = 0; o < NOWN; ++o) ch[o] = chd[o] = 0.f;
+  for (int o = 0; o < NOWN; ++o) {
+    ob[o] = (BT < G) ? ql % BT : o * G + ql;
+    act[o] = (EXACT && BT == 1) || ((EXACT || k < H) && (ob[o] < nb));
+    ch[o] = (p.last_only && act[o]) ? p.hbar[(size_t)(b0 + ob[o]) * H + k] : 0.f;
+    chd[o] = (p.last_only && act[o]) ? p.hdbar[(size_t)(b0 + ob[o]) * H + k] : 0.f;
+  }
   pipe.start();
   __syncthreads();
 
+  const uint32_t dgs_addr = smem_u32(dgs);
+  const uint32_t h_step = 4u * (uint32_t)H, g_step = 12u * (uint32_t)H;
+  const uint32_t lane_k = 16u * (uint32_t)ql;
+  uint32_t a_g[NOWN], a_q[NOWN], a_t[NOWN], a_qd[NOWN], a_h[NOWN], a_hd[NOWN], a_hb[NOWN], a_hdb[NOWN];
+  // coefficient pairs (alpha on hb, beta on hdb) of the step about to be processed
+  float arA[NOWN], arB[NOWN], azA[NOWN], azB[NOWN], anA[NOWN], anB[NOWN], qA[NOWN], qB[NOWN];
+  float ardB[NOWN], azdB[NOWN], andB[NOWN], qdB[NOWN], nhA[NOWN], nhB[NOWN], fhb[NOWN], fhdb[NOWN];
+
+  auto fetch = [&](bool first_t) __attribute__((always_inline)) {
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const float rt = lds_f32(a_g[o]), zt = lds_f32(a_g[o] + h_step), nt = lds_f32(a_g[o] + 2u * h_step);
+      const float qt = lds_f32(a_q[o]);
+      const float art = lds_f32(a_t[o]), azt = lds_f32(a_t[o] + h_step), ant = lds_f32(a_t[o] + 2u * h_step);
+      const float qdt = lds_f32(a_qd[o]);
+      float hp = lds_f32(a_h[o]), hdp = lds_f32(a_hd[o]);
+      hp = first_t ? 0.f : hp;
+      hdp = first_t ? 0.f : hdp;
+      float hb = lds_f32(a_hb[o]), hdb = lds_f32(a_hdb[o]);
+      fhb[o] = use_bar ? hb : 0.f;
+      fhdb[o] = use_bar ? hdb : 0.f;
+      const float sr = rt * (1.f - rt), omz = 1.f - zt, sz = zt * omz, sn = fmaf(-nt, nt, 1.f);
+      const float rdot = sr * art, zdot = sz * azt, ndot = sn * ant, hmn = hp - nt;
+      const float K1 = sn * omz;
+      const float K2 = sn * (-zdot - 2.f * nt * ant * omz);
+      // anb = K1 hb + K2 hdb ; anb_d = K1 hdb
+      anA[o] = K1; anB[o] = K2; andB[o] = K1;
+      qdB[o] = rt * K1;
+      const float rdbB = qt * K1;                       // rdb = rdbB hdb
+      ardB[o] = sr * rdbB;
+      qA[o] = rt * K1; qB[o] = fmaf(rdot, K1, rt * K2);
+      // rb = qdt anb_d + qt anb + (1-2r) a_r rdb
+      arA[o] = sr * (qt * K1);
+      arB[o] = sr * fmaf(qdt, K1, fmaf(qt, K2, (1.f - 2.f * rt) * art * rdbB));
+      azdB[o] = sz * hmn;
+      azA[o] = sz * hmn;
+      azB[o] = sz * ((hdp - ndot) + (1.f - 2.f * zt) * azt * hmn);
+      nhA[o] = zt; nhB[o] = zdot;
+      // nhd = zt hdb (nhA doubles as its coefficient)
+    }
+  };
+
   int par = 0;
+  float nh[NOWN], nhd[NOWN];
+  auto step = [&]() __attribute__((always_inline)) {
+    const uint32_t dg = dgs_addr + (uint32_t)(par * BT * 6 * HR) * 4u;
+#pragma unroll
+    for (int o = 0; o < NOWN; ++o) {
+      const float hb = fhb[o] + ch[o];
+      const float hdb = fhdb[o] + chd[o];
+      const float arb = fmaf(arA[o], hb, arB[o] * hdb);
+      const float azb = fmaf(azA[o], hb, azB[o] * hdb);
+      const float anb = fmaf(anA[o], hb, anB[o] * hdb);
+      const float qb = fmaf(qA[o], hb, qB[o] * hdb);
+      const float arb_d = ardB[o] * hdb, azb_d = azdB[o] * hdb, anb_d = andB[o] * hdb, qdb = qdB[o] * hdb;
+      nh[o] = fmaf(nhA[o], hb, nhB[o] * hdb);
+      nhd[o] = nhA[o] * hdb;
+      if (act[o]) {
+        const uint32_t d = dg + (uint32_t)((ob[o] * 6) * HR + k) * 4u;
+        sts_f32(d, arb); sts_f32(d + HR * 4u, azb); sts_f32(d + 2u * HR * 4u, qb);
+        sts_f32(d + 3u * HR * 4u, arb_d); sts_f32(d + 4u * HR * 4u, azb_d); sts_f32(d + 5u * HR * 4u, qdb);
+        sts_f32(a_g[o], arb); sts_f32(a_g[o] + h_step, azb); sts_f32(a_g[o] + 2u * h_step, anb); sts_f32(a_q[o], qb);
+        sts_f32(a_t[o], arb_d); sts_f32(a_t[o] + h_step, azb_d); sts_f32(a_t[o] + 2u * h_step, anb_d);
+        sts_f32(a_qd[o], qdb);
+      }
+      a_g[o] -= g_step; a_q[o] -= h_step; a_t[o] -= g_step; a_qd[o] -= h_step;
+      a_h[o] -= h_step; a_hd[o] -= h_step; a_hb[o] -= h_step; a_hdb[o] -= h_step;
+    }
+  };
+
   for (int c = 0; c < pipe.NC; ++c) {
     pipe.acquire(c);
     const int s = c % NST;
     const int t0 = pipe.t0_of(c);
     const int tcn = pipe.tcn_of(c);
-    for (int tl = tcn - 1; tl >= 0; --tl) {
-      const int t = t0 + tl;
-      float* dg = dgs + par * BT * 6 * HR;
-      float nh[NOWN], nhd[NOWN];
 #pragma unroll
-      for (int o = 0; o < NOWN; ++o) {
-        const int b = (BT < G) ? ql : o * G + ql;
-        nh[o] = nhd[o] = 0.f;
-        if (k < H && b < nb) {
-          float* gp = pipe.row(s, 0, b, tl);
-          float* qp = pipe.row(s, 1, b, tl);
-          float* tp = pipe.row(s, 2, b, tl);
-          float* qdp = pipe.row(s, 3, b, tl);
-          const float rt = gp[k], zt = gp[H + k], nt = gp[2 * H + k], qt = qp[k];
-          const float art = tp[k], azt = tp[H + k], ant = tp[2 * H + k], qdt = qdp[k];
-          const float hp = (t > 0) ? pipe.row(s, 4, b, tl)[k] : 0.f;
-          const float hdp = (t > 0) ? pipe.row(s, 5, b, tl)[k] : 0.f;
-          float hb, hdb;
-          if (p.last_only) {
-            hb = (t == T - 1) ? p.hbar[(size_t)(b0 + b) * H + k] : 0.f;
-            hdb = (t == T - 1) ? p.hdbar[(size_t)(b0 + b) * H + k] : 0.f;
-          } else {
-            hb = pipe.row(s, 6, b, tl)[k];
-            hdb = pipe.row(s, 7, b, tl)[k];
-          }
-          hb += ch[o];
-          hdb += chd[o];
-          const float sr = rt * (1.f - rt), sz = zt * (1.f - zt), sn = 1.f - nt * nt;
-          const float rdot = sr * art, zdot = sz * azt, ndot = sn * ant;
-          // hdot_t = (1-z) ndot + z hdot_{t-1} + zdot (h_{t-1} - n)
-          const float ndb = (1.f - zt) * hdb;
-          float zb = hdb * (hdp - ndot);
-          const float zdb = hdb * (hp - nt);
-          float nb_ = -zdot * hdb;
-          nh[o] = zdot * hdb;
-          nhd[o] = zt * hdb;
-          // h_t = n + z (h_{t-1} - n)
-          nb_ += (1.f - zt) * hb;
-          zb += hb * (hp - nt);
-          nh[o] += zt * hb;
-          // ndot = (1-n^2) a_n
-          const float anb_d = sn * ndb;
-          nb_ -= 2.f * nt * ant * ndb;
-          // a_n = gid_n + rdot q + r qdot
-          const float rdb = qt * anb_d;
-          float qb = rdot * anb_d;
-          float rb = qdt * anb_d;
-          const float qdb = rt * anb_d;
-          // n = tanh(gi_n + r q)
-          const float anb = sn * nb_;
-          rb += qt * anb;
-          qb += rt * anb;
-          // zdot = sz a_z ; rdot = sr a_r
-          const float azb_d = sz * zdb;
-          zb += (1.f - 2.f * zt) * azt * zdb;
-          const float arb_d = sr * rdb;
-          rb += (1.f - 2.f * rt) * art * rdb;
-          const float azb = sz * zb;
-          const float arb = sr * rb;
-          gp[k] = arb; gp[H + k] = azb; gp[2 * H + k] = anb; qp[k] = qb;
-          tp[k] = arb_d; tp[H + k] = azb_d; tp[2 * H + k] = anb_d; qdp[k] = qdb;
-          float* d0 = dg + (b * 6) * HR;
-          d0[0 * HR + k] = arb;   d0[1 * HR + k] = azb;   d0[2 * HR + k] = qb;
-          d0[3 * HR + k] = arb_d; d0[4 * HR + k] = azb_d; d0[5 * HR + k] = qdb;
-        }
-      }
-      if (tl == 0 && pipe.bulk) fence_async_smem();
+    for (int o = 0; o < NOWN; ++o) {
+      const int b = act[o] ? ob[o] : 0;
+      const uint32_t kk = 4u * (uint32_t)(act[o] ? k : 0);
+      a_g[o] = pipe.row_addr(s, 0, b, tcn - 1) + kk;
+      a_q[o] = pipe.row_addr(s, 1, b, tcn - 1) + kk;
+      a_t[o] = pipe.row_addr(s, 2, b, tcn - 1) + kk;
+      a_qd[o] = pipe.row_addr(s, 3, b, tcn - 1) + kk;
+      a_h[o] = pipe.row_addr(s, 4, b, tcn - 1) + kk;
+      a_hd[o] = pipe.row_addr(s, 5, b, tcn - 1) + kk;
+      a_hb[o] = pipe.row_addr(s, 6, b, tcn - 1) + kk;
+      a_hdb[o] = pipe.row_addr(s, 7, b, tcn - 1) + kk;
+    }
+    fetch(t0 + tcn - 1 == 0);
+    for (int tl = tcn - 1; tl >= 0; --tl) {
+      const bool last = (tl == 0);
+      step();
+      if (last && pipe.bulk) fence_async_smem();
       __syncthreads();
+      if (!last) fetch(t0 + tl - 1 == 0);    // next step's coefficient pairs form behind the mat-vecs below
+      const uint32_t dg = dgs_addr + (uint32_t)(par * BT * 6 * HR) * 4u;
       float2 a2[BT][2][3];
 #pragma unroll
       for (int b = 0; b < BT; ++b)
@@ -341,8 +433,9 @@ __global__ void __launch_bounds__(HP* G, jvp_min_blocks<HP, G>()) gru_jvp_bwd_ke
         for (int g = 0; g < 3; ++g)
 #pragma unroll
           for (int b = 0; b < BT; ++b) {
-            const float4 dv = reinterpret_cast<const float4*>(dg + (b * 6 + g) * HR)[i * G + ql];
-            const float4 ev = reinterpret_cast<const float4*>(dg + (b * 6 + 3 + g) * HR)[i * G + ql];
+            const uint32_t off = (uint32_t)(i * G) * 16u + lane_k;
+            const float4 dv = lds_v4(dg + (uint32_t)((b * 6 + g) * HR) * 4u + off);
+            const float4 ev = lds_v4(dg + (uint32_t)((b * 6 + 3 + g) * HR) * 4u + off);
             a2[b][0][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(dv.x, dv.y), a2[b][0][g]);
             a2[b][1][g] = __ffma2_rn(wt[g][2 * i + 0], make_float2(ev.x, ev.y), a2[b][1][g]);
             a2[b][0][g] = __ffma2_rn(wt[g][2 * i + 1], make_float2(dv.z, dv.w), a2[b][0][g]);
@@ -373,8 +466,10 @@ int launch_jf(cudaStream_t st, const JfParams& p) {
   constexpr int HR = HP + JV_PAD;
   size_t smem = ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<6, BT, TC, NST>::stage_floats_for(widths) * 4;
-  auto kern = gru_jvp_fwd_kernel<HP, G, BT, TC, NST>;
-  TG_OPT_IN_SMEM(kern, "gru_jvp_fwd");
+  const bool exact = (p.H == HP);
+  auto kern = exact ? gru_jvp_fwd_kernel<HP, G, BT, TC, NST, true> : gru_jvp_fwd_kernel<HP, G, BT, TC, NST, false>;
+  if (exact) { TG_OPT_IN_SMEM((gru_jvp_fwd_kernel<HP, G, BT, TC, NST, true>), "gru_jvp_fwd"); }
+  else { TG_OPT_IN_SMEM((gru_jvp_fwd_kernel<HP, G, BT, TC, NST, false>), "gru_jvp_fwd"); }
   if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_jvp_fwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   kern<<<dim3((p.B + BT - 1) / BT), dim3(HP * G), smem, st>>>(p);
   return tg_check_launch("gru_jvp_fwd");
@@ -386,8 +481,10 @@ int launch_jb(cudaStream_t st, const JbParams& p) {
   constexpr int HR = HP + JV_PAD;
   size_t smem = ((2 * BT * 6 * HR * 4 + NST * 8 + 127) / 128) * 128 +
                 (size_t)NST * ChunkPipe<8, BT, TC, NST>::stage_floats_for(widths) * 4;
-  auto kern = gru_jvp_bwd_kernel<HP, G, BT, TC, NST>;
-  TG_OPT_IN_SMEM(kern, "gru_jvp_bwd");
+  const bool exact = (p.H == HP);
+  auto kern = exact ? gru_jvp_bwd_kernel<HP, G, BT, TC, NST, true> : gru_jvp_bwd_kernel<HP, G, BT, TC, NST, false>;
+  if (exact) { TG_OPT_IN_SMEM((gru_jvp_bwd_kernel<HP, G, BT, TC, NST, true>), "gru_jvp_bwd"); }
+  else { TG_OPT_IN_SMEM((gru_jvp_bwd_kernel<HP, G, BT, TC, NST, false>), "gru_jvp_bwd"); }
   if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_jvp_bwd: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
   kern<<<dim3((p.B + BT - 1) / BT), dim3(HP * G), smem, st>>>(p);
   return tg_check_launch("gru_jvp_bwd");
