@@ -200,3 +200,38 @@ def test_side_stream_weight_gradients_equal_inline():
     assert torch.equal(dx0, dx1)
     for a, b in zip(g0, g1):
         assert relerr(b, a) < 1e-5
+
+
+def test_inter_layer_dropout_masks_forward_and_bptt():
+    """nn.GRU(dropout=p) feeds layer l+1 with y_l * mask_l in train mode (timegan_model.py:27-30).  With the masks
+    given, forward and BPTT must equal a stack of single-layer torch GRUs with the same masks under autograd."""
+    ops = _ops()
+    B, T, I, H, L = 5, 48, 14, 24, 3
+    m = make_gru(I, H, L, seed=21)
+    g = torch.Generator().manual_seed(8)
+    x = torch.rand(B, T, I, generator=g, requires_grad=True)
+    dy = torch.randn(B, T, H, generator=g)
+    masks = [(torch.rand(B, T, H, generator=g) > 0.3).float() / 0.7 for _ in range(L - 1)]
+    layers = []
+    for l in range(L):
+        one = torch.nn.GRU(I if l == 0 else H, H, 1, batch_first=True)
+        with torch.no_grad():
+            for name in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                getattr(one, name + "_l0").copy_(getattr(m, f"{name}_l{l}"))
+        layers.append(one)
+    h = x
+    for l, one in enumerate(layers):
+        h, _ = one(h)
+        if l < L - 1:
+            h = h * masks[l]
+    params = [p for one in layers for p in (one.weight_ih_l0, one.weight_hh_l0, one.bias_ih_l0, one.bias_hh_l0)]
+    ref = torch.autograd.grad((h * dy).sum(), [x] + params)
+    dev = torch.device("cuda:0")
+    w = flat_weights(m, dev)
+    md = [mk.to(dev) for mk in masks]
+    y, saves = ops.stack_forward(x.detach().to(dev), w, save=True, masks=md)
+    assert relerr(y, h.detach()) < TOL
+    dx, grads = ops.stack_backward(dy.to(dev), saves, w, need_dx=True, need_dw=True, masks=md)
+    assert relerr(dx, ref[0]) < TOL
+    for k, gk in enumerate(grads):
+        assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"

@@ -33,13 +33,27 @@ def test_peer_site_sizes_and_argument_checks():
     assert lib.tg_peer_allreduce(None, 0, 2, regions, 0, 0, 256, 256, 49, ptrs, one) < 0      # too many tensors
 
 
+def _torchrun2(tool, port):
+    env = dict(os.environ, PYTHONPATH=str(ROOT))
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(ROOT / "tools" / tool)],
+                          capture_output=True, text=True, env=env, timeout=400)
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box")
 def test_peer_allreduce_matches_nccl_two_ranks():
-    env = dict(os.environ, PYTHONPATH=str(ROOT))
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29533",
-                        str(ROOT / "tools" / "check_peer_allreduce.py")], capture_output=True, text=True, env=env,
-                       timeout=300)
+    r = _torchrun2("check_peer_allreduce.py", 29533)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count(": OK") == 2
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box")
+def test_dp_equals_single_process_and_graph_equals_eager_two_ranks():
+    """DP on two ranks == one process on the global batch, and the DP step replayed from the CUDA
+    graph (peer all-reduce kernels inside the graph) == the DP step issued eagerly."""
+    r = _torchrun2("check_dp_equivalence.py", 29534)
+    assert r.returncode == 0 and r.stdout.count("-> OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+    r = _torchrun2("check_dp_graph.py", 29535)
+    assert r.returncode == 0 and r.stdout.count("-> OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]

@@ -111,6 +111,49 @@ def test_joint_steps_match_oracle_port_live(cfg):
         assert (p.detach().cpu() - q.detach()).abs().max().item() < 0.1 * 1e-3, n
 
 
+def test_joint_step_bf16_projection_mode_within_2e_2():
+    """north_star: "bf16 projection mode within 2e-2".  The reduced-precision projection mode (one TF32 tensor-core
+    pass over the fp32 operands, ops.set_proj_mode("bf16")) against the fp32 CPU port on one D + G update at the
+    config-c2/c3 layer shape (z = h = 64, 3 layers; T*B >= 128 rows so the tcgen05 tile is really taken)."""
+    import timegan_b200 as tg
+    from timegan_b200 import ops, train_timegan as tt
+    from oracle import timegan_ref as R
+    torch.manual_seed(5)
+    port = R.build_model(14, 64, 64, 3, 0.0)
+    ours = tg.TimeGAN(14, 64, 64, 3, 0.0)
+    ours.load_state_dict(port.state_dict())
+    ours = ours.to(DEV)
+    x = torch.rand(4, 96, 14)
+    op = R.make_optimizers(port)
+    oD = tg.FusedAdam(ours.discriminator.parameters(), lr=2e-4, betas=(0.5, 0.9))
+    oG = tg.FusedAdam(tt._params(ours.generator, ours.supervisor, ours.embedder, ours.recovery), lr=1e-3, betas=(0.5, 0.9))
+    old = ops.get_proj_mode()
+    try:
+        ops.set_proj_mode("bf16")
+        torch.manual_seed(21)
+        d_p = R.d_step(port, x, op["D"], R.TorchNoise(), 0.2, 0.3, 0.5, 1.0, 0.525, 0.15)
+        torch.manual_seed(21)
+        nz = tt.HostReplayNoise(DEV)
+        d_o = tt.disc_step(ours, x.to(DEV), DEV, oD, 0.2, 0.3, 0.5, None, 1.0, target_acc=0.525, band=0.15, noise=nz)
+        state = torch.get_rng_state()
+        g_p = R.g_step(port, x, op["G"], R.TorchNoise(), 5.0, 0.2, 0.3, 0.5, 0.05, 0.05, 32)
+        torch.set_rng_state(state)
+        g_o = tt.gen_step(ours, x.to(DEV), DEV, oG, 5.0, 0.2, 0.3, 0.5, None, 0.05, 0.05, 32, noise=nz)
+    finally:
+        ops.set_proj_mode(old)
+    assert _close(d_o[0], d_p[0], 2e-2), (d_o, d_p)
+    for a, b in zip(g_o, g_p):
+        assert _close(a, b, 2e-2), (g_o, g_p)
+    # Adam's first step moves every weight by +-lr whatever |g| is, so a 5e-4 relative gradient error may flip the
+    # sign of a near-zero entry: bound the FRACTION of weights that moved differently, not the maximum
+    bad = tot = 0
+    for (n, p), (_, q) in zip(ours.named_parameters(), port.named_parameters()):
+        d = (p.detach().cpu() - q.detach()).abs()
+        bad += int((d > 0.5e-3).sum())
+        tot += d.numel()
+    assert bad / tot < 0.02, (bad, tot)
+
+
 def test_generation_chain_matches_port():
     """decode(refine_latent(gen_latent(Z))) in eval mode, chunked (generate_long_synth.py:117-121)."""
     import timegan_b200 as tg
