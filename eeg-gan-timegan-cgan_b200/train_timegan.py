@@ -20,6 +20,7 @@ There is no CPU path: a CPU tensor or a missing libtimegan_b200.so raises.
 """
 import csv
 import math
+import os
 from pathlib import Path
 from typing import Dict, Optional, Tuple
 
@@ -56,6 +57,37 @@ def make_loader(X: np.ndarray, batch_size: int) -> DataLoader:
     tens = torch.tensor(X, dtype=torch.float32)
     ds = TensorDataset(tens)
     return DataLoader(ds, batch_size=batch_size, shuffle=True, drop_last=False, pin_memory=True, num_workers=0)
+
+
+class DeviceLoader:
+    """`make_loader` (tt:33-37) with the dataset resident in HBM.
+
+    At B200 speeds a joint step takes ~24 ms, and the whole dataset (N x 768 x 14 fp32: 11 MB for N=256, 1.4 GB for
+    N=32 768) fits the device many times over, so the per-batch collate + pin + H2D copy of the DataLoader is pure
+    overhead: X is uploaded once and a batch is one on-device gather.  The ORDER is the reference's: an epoch's
+    permutation is drawn exactly like DataLoader(shuffle=True) draws it -- `_base_seed` then the RandomSampler's
+    seed, two int64 draws from the global CPU generator, then randperm from a private generator -- so runs that
+    replay the CPU random stream (noise="host") see the same batches AND leave the global generator in the same
+    state as the reference.  drop_last=False: the ragged last batch is yielded as is.  Yields 1-tuples like a
+    DataLoader over a TensorDataset."""
+
+    def __init__(self, X, batch_size: int, device):
+        self.X = torch.as_tensor(X, dtype=torch.float32).to(device).contiguous()
+        self.batch_size = int(batch_size)
+        self.device = self.X.device
+
+    def __len__(self):
+        return (self.X.shape[0] + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        n = self.X.shape[0]
+        torch.empty((), dtype=torch.int64).random_()                       # DataLoader iterator's _base_seed
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())    # RandomSampler's private seed
+        gen = torch.Generator()
+        gen.manual_seed(seed)
+        perm = torch.randperm(n, generator=gen).to(self.device, non_blocking=True)
+        for i in range(0, n, self.batch_size):
+            yield (self.X.index_select(0, perm[i:i + self.batch_size]),)
 
 
 class HostReplayNoise:
@@ -158,6 +190,65 @@ def save_ckpt(path: Path, model: TimeGAN, optG, optD, step: int, meta: Dict):
     state = {"step": step, "model": model.state_dict(), "optG": optG.state_dict(), "optD": optD.state_dict(),
              "meta": meta}
     torch.save(state, path)
+
+
+class AsyncCheckpointer:
+    """`save_ckpt` (tt:58-61) without stalling the training stream.
+
+    save() snapshots every tensor of the checkpoint dict into pinned host memory with non-blocking copies on the
+    current stream (so the snapshot is the state at that point of the stream, whatever the GPU does next), records
+    an event and hands the dict to a writer thread, which waits for the event and calls torch.save -- same dict,
+    same schema {"step","model","optG","optD","meta"}, loadable by the reference's tools.  One write at a time:
+    a new save() first joins the previous one.  wait() joins the writer (call before reading the file)."""
+
+    def __init__(self):
+        self._thread = None
+        self._error = None
+
+    @staticmethod
+    def _snapshot(obj):
+        if torch.is_tensor(obj):
+            if obj.is_cuda:
+                host = torch.empty(obj.shape, dtype=obj.dtype, pin_memory=True)
+                host.copy_(obj.detach(), non_blocking=True)
+                return host
+            return obj.detach().clone()
+        if isinstance(obj, dict):
+            return type(obj)((k, AsyncCheckpointer._snapshot(v)) for k, v in obj.items())
+        if isinstance(obj, (list, tuple)):
+            return type(obj)(AsyncCheckpointer._snapshot(v) for v in obj)
+        return obj
+
+    def save(self, path: Path, model: TimeGAN, optG, optD, step: int, meta: Dict):
+        self.wait()
+        state = self._snapshot({"step": step, "model": model.state_dict(), "optG": optG.state_dict(),
+                                "optD": optD.state_dict(), "meta": dict(meta)})
+        ev = None
+        if torch.cuda.is_available():
+            ev = torch.cuda.Event()
+            ev.record()
+
+        def _write():
+            try:
+                if ev is not None:
+                    ev.synchronize()
+                tmp = Path(str(path) + ".tmp")
+                torch.save(state, tmp)
+                os.replace(tmp, path)          # never leave a half-written checkpoint behind
+            except Exception as e:  # pragma: no cover
+                self._error = e
+
+        import threading
+        self._thread = threading.Thread(target=_write, daemon=True)
+        self._thread.start()
+
+    def wait(self):
+        if self._thread is not None:
+            self._thread.join()
+            self._thread = None
+        if self._error is not None:
+            e, self._error = self._error, None
+            raise e
 
 
 def sample_noise(batch_size: int, seq_len: int, z_dim: int, device, noise=None):
@@ -555,13 +646,21 @@ def train_single_npz(npz_path: Path, out_dir: Path,
                      noise: Optional[str] = None,
                      proj_dtype: str = "fp32",
                      log_every: int = 1,
-                     graph: bool = False):
+                     graph: bool = False,
+                     resident_data: bool = True,
+                     resume: bool = False,
+                     ckpt_every: int = 500,
+                     stop_after: Optional[int] = None):
     """Same schedule, logs and artefacts as the reference.  Extras (keyword-only): `z_dim`/`hidden_dim`
     override adaptive_dims; `noise="host"` replays the reference's CPU random stream (parity runs), default is
     on-device Philox; `proj_dtype` "fp32" | "bf16" (tensor-core input projections); `log_every` k > 1 keeps
     the per-step scalars on the device and flushes CSV rows / best-checkpoint decisions every k steps;
     `graph=True` replays the joint step from a CUDA graph (GraphedJointStep; full-size batches only -- the ragged
-    last batch of an epoch runs eagerly -- on-device noise, one GPU)."""
+    last batch of an epoch runs eagerly -- on-device noise); `resident_data` keeps the dataset in HBM and gathers
+    batches on the device in the reference's shuffle order (DeviceLoader); `resume=True` continues the GAN phase
+    from `out_dir/ckpt_latest.pt` (weights, both optimisers, LR schedules, noise decay, step counter) instead of
+    starting over -- the reference can only start over; `ckpt_every` is the reference's hard-coded 500 (tt:406);
+    `stop_after=k` ends the run after GAN step k with a checkpoint written (pre-emption / tests)."""
     npz_path, out_dir = Path(npz_path), Path(out_dir)
     set_seeds(seed)
     device = device or device_autoselect()
@@ -580,7 +679,11 @@ def train_single_npz(npz_path: Path, out_dir: Path,
     h_dim = int(hidden_dim) if hidden_dim is not None else hd
 
     log_file = out_dir / "train_log.csv"
-    if rank0:
+    ckpt_path, best_path = out_dir / "ckpt_latest.pt", out_dir / "ckpt_best.pt"
+    resume_state = None
+    if resume and ckpt_path.exists():
+        resume_state = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    if rank0 and not (resume_state is not None and log_file.exists()):
         with open(log_file, "w", newline="") as f:
             csv.writer(f).writerow(["step", "phase", "loss_D", "acc_D", "loss_G", "loss_adv", "loss_sup", "loss_rec",
                                     "loss_cov", "loss_acf"])
@@ -591,15 +694,22 @@ def train_single_npz(npz_path: Path, out_dir: Path,
 
     LOG(f"==> {npz_path.name} | N={N} T={T} C={C}  z_dim={z_dim} h_dim={h_dim}  device={device}")
 
-    loader = make_loader(X, batch_size)
+    loader = DeviceLoader(X, batch_size, device) if resident_data else make_loader(X, batch_size)
     model = TimeGAN(x_dim=C, z_dim=z_dim, hidden_dim=h_dim, num_layers=layers, dropout=dropout).to(device)
     nz = HostReplayNoise(device) if noise == "host" else None
 
-    optER = FusedAdam(_params(model.embedder, model.recovery), lr=lr_g, betas=betas)
-    phase_autoencoder(model, loader, device, optER, grad_clip, ae_epochs, LOG)
+    start_step = 0
+    if resume_state is not None:
+        # the checkpoint was written during the GAN phase: phases 1 and 2 are behind us
+        model.load_state_dict(resume_state["model"])
+        start_step = int(resume_state["step"])
+        LOG(f"[resume] {ckpt_path.name}: continuing the GAN phase after step {start_step}/{gan_steps}")
+    else:
+        optER = FusedAdam(_params(model.embedder, model.recovery), lr=lr_g, betas=betas)
+        phase_autoencoder(model, loader, device, optER, grad_clip, ae_epochs, LOG)
 
-    optS = FusedAdam(model.supervisor.parameters(), lr=lr_g, betas=betas)
-    phase_supervisor(model, loader, device, optS, grad_clip, sup_epochs, LOG)
+        optS = FusedAdam(model.supervisor.parameters(), lr=lr_g, betas=betas)
+        phase_supervisor(model, loader, device, optS, grad_clip, sup_epochs, LOG)
 
     # under data parallelism the step can only be captured when the all-reduces are this package's own peer-memory
     # kernels (dist.PeerComm); NCCL collectives are issued eagerly
@@ -607,15 +717,36 @@ def train_single_npz(npz_path: Path, out_dir: Path,
     optD = FusedAdam(model.discriminator.parameters(), lr=lr_d, betas=betas, capturable=use_graph)
     optG = FusedAdam(_params(model.generator, model.supervisor, model.embedder, model.recovery), lr=lr_g, betas=betas,
                      capturable=use_graph)
+    if resume_state is not None:
+        optG.load_state_dict(resume_state["optG"])
+        optD.load_state_dict(resume_state["optD"])
+        for opt in (optG, optD):       # Adam moments back onto the device; the base LR is re-derived below
+            for st in opt.state.values():
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if k in st:
+                        st[k] = st[k].to(device)
+            for g in opt.param_groups:
+                g["lr"] = g.get("initial_lr", g["lr"])
     milestones = [gan_steps // 2, int(gan_steps * 0.75)]
     schedulerG = optim.lr_scheduler.MultiStepLR(optG, milestones=milestones, gamma=0.5)
     schedulerD = optim.lr_scheduler.MultiStepLR(optD, milestones=milestones, gamma=0.5)
+    if start_step:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for _ in range(start_step):     # one scheduler tick per completed GAN step (tt:348-349)
+                schedulerG.step()
+                schedulerD.step()
 
+    step_noise = nz
+    if start_step and nz is None:
+        # a fresh Philox stream for the continued run (the default stream would restart at its first draw)
+        step_noise = device_noise(torch.initial_seed() + 7919 * _dist.rank() + 104729 * start_step, device)
     loader_iter = iter(loader)
-    inst_noise = inst_noise_start
     noise_decay = (inst_noise_start - inst_noise_end) / max(1, gan_steps)
+    inst_noise = max(inst_noise_end, inst_noise_start - noise_decay * start_step)
     best_ckpt_loss = math.inf
-    ckpt_path, best_path = out_dir / "ckpt_latest.pt", out_dir / "ckpt_best.pt"
+    saver = AsyncCheckpointer()
     meta = {"npz": npz_path.name, "z_dim": z_dim, "h_dim": h_dim}
     target = 0.5 * (d_min_acc + d_max_acc)
     band = max(0.0, d_max_acc - d_min_acc)
@@ -625,7 +756,7 @@ def train_single_npz(npz_path: Path, out_dir: Path,
         graphed = GraphedJointStep(model, optD, optG, device, label_smooth=label_smooth, clip=grad_clip,
                                    r1_gamma=r1_gamma, target_acc=target, band=band, alpha_sup=alpha_sup,
                                    beta_rec=beta_rec, gamma_cov=gamma_cov, gamma_acf=gamma_acf, acf_max_lag=acf_max_lag,
-                                   schedulerD=schedulerD, schedulerG=schedulerG)
+                                   schedulerD=schedulerD, schedulerG=schedulerG, noise=step_noise)
 
     def flush():
         nonlocal best_ckpt_loss
@@ -649,7 +780,7 @@ def train_single_npz(npz_path: Path, out_dir: Path,
         best_ckpt_loss = min([best_ckpt_loss] + [r[4] for r in rows])
         pending.clear()
 
-    for step in range(1, gan_steps + 1):
+    for step in range(start_step + 1, gan_steps + 1):
         try:
             (x_batch,) = next(loader_iter)
         except StopIteration:
@@ -662,17 +793,24 @@ def train_single_npz(npz_path: Path, out_dir: Path,
             pending.append((step, tuple(vals.unbind(0))))
         else:
             d_loss, d_acc = disc_step(model, x, device, optD, label_smooth, inst_noise, grad_clip, schedulerD, r1_gamma,
-                                      target_acc=target, band=band, noise=nz, sync=False)
+                                      target_acc=target, band=band, noise=step_noise, sync=False)
             g_vals = gen_step(model, x, device, optG, alpha_sup, beta_rec, inst_noise, grad_clip, schedulerG, gamma_cov,
-                              gamma_acf, acf_max_lag, noise=nz, sync=False)
+                              gamma_acf, acf_max_lag, noise=step_noise, sync=False)
             pending.append((step, (d_loss, d_acc) + tuple(g_vals)))
         if len(pending) >= max(1, log_every) or step == gan_steps:
             flush()
 
         inst_noise = max(inst_noise_end, inst_noise - noise_decay)
-        if (step % 500 == 0 or step == gan_steps) and rank0:
+        stopping = stop_after is not None and step >= stop_after
+        if (step % max(1, ckpt_every) == 0 or step == gan_steps or stopping) and rank0:
             flush()
-            save_ckpt(ckpt_path, model, optG, optD, step, meta)
+            saver.save(ckpt_path, model, optG, optD, step, meta)     # written behind the training stream
+        if stopping:
+            flush()
+            saver.wait()
+            LOG(f"[stop] stop_after={stop_after}: checkpoint at step {step}, resume with resume=True")
+            return
+    saver.wait()
 
     model.eval()
     from .generate_long_synth import generate_windows
@@ -721,6 +859,8 @@ def build_argparser():
     ap.add_argument("--noise", type=str, default=None, choices=[None, "host"])
     ap.add_argument("--log_every", type=int, default=1)
     ap.add_argument("--graph", action="store_true", help="replay the joint step from a CUDA graph")
+    ap.add_argument("--resume", action="store_true", help="continue the GAN phase from <out_dir>/ckpt_latest.pt")
+    ap.add_argument("--ckpt_every", type=int, default=500, help="GAN steps between ckpt_latest.pt writes")
     return ap
 
 
@@ -744,7 +884,8 @@ def main(argv=None):
             layers=args.layers, dropout=args.dropout, seed=args.seed, r1_gamma=args.r1_gamma,
             d_min_acc=args.d_min_acc, d_max_acc=args.d_max_acc, gamma_cov=args.gamma_cov, gamma_acf=args.gamma_acf,
             acf_max_lag=args.acf_max_lag, device=device, z_dim=args.z_dim, hidden_dim=args.hidden_dim,
-            proj_dtype=args.proj_dtype, noise=args.noise, log_every=args.log_every, graph=args.graph)
+            proj_dtype=args.proj_dtype, noise=args.noise, log_every=args.log_every, graph=args.graph,
+            resume=args.resume, ckpt_every=args.ckpt_every)
 
 
 if __name__ == "__main__":
