@@ -59,6 +59,7 @@ SIGNATURES = {
     "tg_acf_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "tg_acf_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "tg_acf_bwd_final": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i]),
+    "tg_acf_score": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "tg_sumsq_workspace_bytes": (_sz, [_i, C.POINTER(_ll)]),
     "tg_sumsq": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_ll), _vp, _vp, _sz]),
     "tg_adam": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _vp,

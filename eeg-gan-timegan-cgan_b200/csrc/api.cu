@@ -302,6 +302,11 @@ int tg_acf_bwd_final(void* stream, const float* gz, const float* xz, const float
   return tg_acf_bwd_final_impl((cudaStream_t)stream, gz, xz, mean_gz, kc, inv_s, dx, rows, C, accumulate);
 }
 
+int tg_acf_score(void* stream, const float* x, int N, int T, int C, int maxlag, double* out) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
+  return tg_acf_score_impl((cudaStream_t)stream, x, N, T, C, maxlag, out);
+}
+
 size_t tg_colsum_workspace_bytes(int N) { return tg_colsum_ws_bytes(N); }
 int tg_colsum(void* stream, const float* X, int ld, int M, int N, float* out, int accumulate, void* ws,
               size_t ws_bytes) {

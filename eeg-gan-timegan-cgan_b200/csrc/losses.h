@@ -19,6 +19,9 @@ int tg_acf_bwd_impl(cudaStream_t st, const float* xz, const float* S, int B, int
 int tg_acf_bwd_final_impl(cudaStream_t st, const float* gz, const float* xz, const float* mg, const float* kc,
                           const float* inv_s, float* dx, long long rows, int C, int accumulate);
 
+// evaluation statistics (eval_stats.cu)
+int tg_acf_score_impl(cudaStream_t st, const float* x, int N, int T, int C, int maxlag, double* out);
+
 // optimiser
 #define TG_MT_MAX 48   // tensors per multi-tensor launch
 int tg_sumsq_multi_impl(cudaStream_t st, int n, const float* const* grads, const long long* sizes, float* out_sumsq,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 6
+#define TG_ABI_VERSION 7
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -135,6 +135,11 @@ int tg_acf_bwd(void* stream, const float* xz, const float* S /* (L,C) */, int B,
                float* gz /* (B,T,C) */, float* stat /* (B,2,C) */);
 int tg_acf_bwd_final(void* stream, const float* gz, const float* xz, const float* mean_gz, const float* kc,
                      const float* inv_s, float* dx, long long rows, int C, int accumulate);
+
+/* ---- evaluation statistics (timeGAN/evaluation.py:63-71,126-131) --------------------------------
+ * out[n*C + c] (fp64) = autocorr_seq(x[n,:,c], maxlag): 0 if std < 1e-8, else the mean over lag = 1..min(maxlag,T-1)
+ * of the Pearson correlation of x[:-lag] and x[lag:] (each slice with its own mean / variance, like np.corrcoef). */
+int tg_acf_score(void* stream, const float* x /* (N,T,C) */, int N, int T, int C, int maxlag, double* out /* (N,C) */);
 
 /* ---- clip_grad_norm_ + Adam (train_timegan.py:141-142,160-161,220-221,268-272) ---------------------------
  * Host arrays of n device pointers / element counts.  tg_sumsq writes sum g^2 over all tensors to a device
