@@ -80,3 +80,33 @@ def test_posthoc_networks_match_reference():
     torch.manual_seed(2)
     rmse, r2 = ev.predictive_score(real[:, :-1], real[:, -1], fake[:, :-1], fake[:, -1])
     assert abs(rmse - g["pred_trts"][0]) < 1e-3 * g["pred_trts"][0] and abs(r2 - g["pred_trts"][1]) < 5e-3
+
+
+@pytest.mark.gpu
+def test_evaluation_entry_points_write_the_reference_csvs(tmp_path):
+    """evaluation.main (ev:170-238) and evaluate_18.main (e18:175-262) on a two-posture toy layout: same file names
+    and columns as the reference's CSVs; evaluate_18 prefers synthetic_long.npz (e18:146-152)."""
+    import pandas as pd
+    from timegan_b200 import evaluation as ev, evaluate_18 as e18
+    from oracle.make_golden_eval import make_inputs
+    real_dir, synth_dir = tmp_path / "preprocessed", tmp_path / "timegan_runs"
+    real_dir.mkdir()
+    for p, cond, seed in ((1, "with_exo", 1), (1, "no_exo", 2), (3, "no_exo", 3)):
+        r, f = make_inputs(seed=seed, n=14, T=300)
+        np.savez(real_dir / f"posture{p}_{cond}.npz", X=r, fs=128.0)
+        run = synth_dir / f"posture{p}_{cond}"
+        run.mkdir(parents=True)
+        np.savez(run / "synthetic.npz", X=f)
+    np.savez(synth_dir / "posture3_no_exo" / "synthetic_long.npz", X=make_inputs(seed=9, n=20, T=300)[1])
+    cols = ["disc_acc", "disc_auc", "rmse_tstr", "r2_tstr", "rmse_trts", "r2_trts", "psd_diff", "acf_diff", "coh_diff",
+            "n_real", "n_fake", "seq_len", "n_ch"]
+    ev.main(["--real_dir", str(real_dir), "--synth_dir", str(synth_dir), "--out", str(tmp_path / "o1")])
+    per = pd.read_csv(tmp_path / "o1" / "metrics_per_posture.csv")
+    assert list(per.columns) == ["posture"] + cols and list(per["posture"]) == [1, 3]
+    assert list(per["n_real"]) == [28, 14]                      # posture 1: both conditions concatenated
+    glob = pd.read_csv(tmp_path / "o1" / "metrics_global.csv")
+    assert list(glob.columns) == cols and int(glob["n_real"][0]) == 42 and np.isfinite(glob.values).all()
+    e18.main(["--real_dir", str(real_dir), "--synth_dir", str(synth_dir), "--out", str(tmp_path / "o2")])
+    per = pd.read_csv(tmp_path / "o2" / "metrics_per_posture_condition.csv")
+    assert list(per.columns) == ["posture", "condition"] + cols and len(per) == 3
+    assert e18.find_synth_npz(synth_dir / "posture3_no_exo").name == "synthetic_long.npz"
