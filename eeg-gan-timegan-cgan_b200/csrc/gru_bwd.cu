@@ -258,14 +258,14 @@ int launch_bwd(cudaStream_t st, const BwdParams& p) {
 
 template <int HP, int G>
 int dispatch_bt(cudaStream_t st, const BwdParams& p, int bt) {
-  constexpr int TC = (HP >= 128) ? 4 : 8, NST = 3;
+  constexpr int TC = 8, NST = 3;   // 8-step chunks (H = 128 used 4: twice the per-chunk ring cost per step)
   // one sequence per CTA (the co-resident, latency-bound regime): 16-step chunks halve the per-chunk cost of the
   // bulk-copy ring (thread 0 issues the stores/loads while the other warps wait at the next barrier)
   if (HP <= 64 && bt == 1 && tg_long_chunks()) return launch_bwd<HP, G, 1, 2 * TC, NST>(st, p);
   switch (bt) {
     case 1: return launch_bwd<HP, G, 1, TC, NST>(st, p);
     case 2: return launch_bwd<HP, G, 2, TC, NST>(st, p);
-    case 4: return launch_bwd<HP, G, 4, TC, NST>(st, p);
+    case 4: return launch_bwd<HP, G, 4, (HP >= 128) ? 4 : TC, NST>(st, p);   // four H=128 sequences x 8 steps x 3 stages exceed shared memory
   }
   tg_set_error("gru_bwd: bad BT %d", bt);
   return TG_ERR_ARG;
