@@ -347,15 +347,21 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
     side.join()
 
 
-def alloc_like_flat(tensors: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+class FlatList(list):
+    """List of views carved out of ONE allocation (`.flat`): whole-set operations are a single launch."""
+    flat: torch.Tensor = None
+
+
+def alloc_like_flat(tensors: Sequence[torch.Tensor]) -> "FlatList":
     """One allocation carved into views shaped like `tensors` (weight-gradient buffers of a stack)."""
     total = sum(t.numel() for t in tensors)
     flat = torch.empty(total, dtype=torch.float32, device=tensors[0].device)
-    out, o = [], 0
+    out, o = FlatList(), 0
     for t in tensors:
         n = t.numel()
         out.append(flat[o:o + n].view(t.shape))
         o += n
+    out.flat = flat
     return out
 
 

@@ -474,11 +474,10 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
             with fork_f:                                   # BPTT of the fake half || reverse-over-tangent of the real half
                 ops.stack_backward(gyf, saves_f, wd, need_dx=False, need_dw=True, dy_last=True, grads=grads_f,
                                    accumulate=False, masks=masks_f)
-            for gt in grads:
-                gt.zero_()
+            grads.flat.zero_()            # one launch for the whole stack (the buffers are views of one allocation)
             ops.stack_jvp_backward(gyr, ghd, saves_r, tsaves, wd, grads, accumulate=True, masks=masks_r)
             fork_f.join()
-            torch._foreach_add_(grads, grads_f)
+            grads.flat.add_(grads_f.flat)
         else:
             ops.stack_backward(torch.cat([gyr, gyf], 0), saves, wd, need_dx=False, need_dw=True, dy_last=True,
                                grads=grads, accumulate=False, masks=masks)
