@@ -66,6 +66,7 @@ SIGNATURES = {
                      _f, _f, _f, _f, _f, _i, _f, _vp]),
     "tg_rng_uniform": (_i, [_vp, _vp, _ll, _ull, _ull, _f, _f, _vp]),
     "tg_rng_add_normal": (_i, [_vp, _vp, _vp, _ll, _f, _ull, _ull, _vp]),
+    "tg_rng_add_normal_dev": (_i, [_vp, _vp, _vp, _ll, _vp, _ull, _ull, _vp]),
     "tg_peer_chunk_floats": (_i, []),
     "tg_peer_alloc": (_i, [C.POINTER(_vp), _sz]),
     "tg_peer_free": (_i, [_vp]),

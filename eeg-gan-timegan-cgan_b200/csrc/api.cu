@@ -336,7 +336,13 @@ int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long see
 int tg_rng_add_normal(void* stream, const float* in, float* out, long long n, float std, unsigned long long seed,
                       unsigned long long offset, const unsigned long long* ctr) {
   ProfScope _ps(stream, K_RNG, 8.0 * (double)n, 0.0);
-  return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, std, seed, offset, ctr);
+  return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, std, seed, offset, ctr, nullptr);
+}
+int tg_rng_add_normal_dev(void* stream, const float* in, float* out, long long n, const float* std_dev,
+                          unsigned long long seed, unsigned long long offset, const unsigned long long* ctr) {
+  ProfScope _ps(stream, K_RNG, 8.0 * (double)n, 0.0);
+  TG_REQUIRE(std_dev, TG_ERR_ARG, "rng_add_normal_dev: null std pointer");
+  return tg_rng_add_normal_impl((cudaStream_t)stream, in, out, n, 0.f, seed, offset, ctr, std_dev);
 }
 
 }  // extern "C"

@@ -34,4 +34,5 @@ int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float
 int tg_rng_uniform_impl(cudaStream_t st, float* out, long long n, unsigned long long seed, unsigned long long offset,
                         float lo, float hi, const unsigned long long* ctr);
 int tg_rng_add_normal_impl(cudaStream_t st, const float* in, float* out, long long n, float std,
-                           unsigned long long seed, unsigned long long offset, const unsigned long long* ctr);
+                           unsigned long long seed, unsigned long long offset, const unsigned long long* ctr,
+                           const float* std_dev);

@@ -48,8 +48,10 @@ __global__ void uniform_kernel(float* __restrict__ out, long long n, uint64_t se
 }
 
 __global__ void add_normal_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, float std,
-                                  uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ ctr) {
+                                  uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ ctr,
+                                  const float* __restrict__ std_dev) {
   if (ctr) offset += *ctr;
+  if (std_dev) std = *std_dev;     // CUDA-graph replay: the instance-noise level decays every step, the graph does not change
   const long long n4 = (n + 3) / 4;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += stride) {
@@ -90,8 +92,9 @@ int tg_rng_uniform_impl(cudaStream_t st, float* out, long long n, unsigned long 
 }
 
 int tg_rng_add_normal_impl(cudaStream_t st, const float* in, float* out, long long n, float std,
-                           unsigned long long seed, unsigned long long offset, const unsigned long long* ctr) {
+                           unsigned long long seed, unsigned long long offset, const unsigned long long* ctr,
+                           const float* std_dev) {
   TG_REQUIRE(out && n > 0, TG_ERR_ARG, "rng_add_normal: bad arguments");
-  add_normal_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(in, out, n, std, seed, offset, ctr);
+  add_normal_kernel<<<blocks_for((n + 3) / 4), 256, 0, st>>>(in, out, n, std, seed, offset, ctr, std_dev);
   return tg_check_launch("rng_add_normal");
 }

@@ -17,15 +17,27 @@ def uniform(shape, device, seed: int, offset: int, lo: float = 0.0, hi: float = 
     return out
 
 
-def add_normal(h: torch.Tensor, std: float, seed: int, offset: int, ctr=None) -> torch.Tensor:
-    """h + std*N(0,1); returns h itself when std <= 0 (tt:46-47)."""
-    if std <= 0:
-        return h
+def add_normal(h: torch.Tensor, std, seed: int, offset: int, ctr=None, out=None) -> torch.Tensor:
+    """h + std*N(0,1) in ONE kernel (tt:46-47).  `std` is a float (returns h itself when <= 0) or a 0-dim device
+    tensor (CUDA-graph replay); `out` may be a contiguous view to write into (e.g. one half of a [real;fake] batch)."""
+    dev_std = torch.is_tensor(std)
+    if not dev_std and std <= 0:
+        if out is None:
+            return h
+        out.copy_(h)
+        return out
     require_cuda(h, "instance-noise input")
     h = h.contiguous()
-    out = torch.empty_like(h)
-    check(lib.tg_rng_add_normal(stream_ptr(), ptr(h), ptr(out), h.numel(), float(std), seed, offset, ptr(ctr)),
-          "tg_rng_add_normal")
+    if out is None:
+        out = torch.empty_like(h)
+    elif not (out.is_contiguous() and out.shape == h.shape):
+        raise ValueError("add_normal: `out` must be a contiguous tensor of the input's shape")
+    if dev_std:
+        check(lib.tg_rng_add_normal_dev(stream_ptr(), ptr(h), ptr(out), h.numel(), ptr(std), seed, offset, ptr(ctr)),
+              "tg_rng_add_normal_dev")
+    else:
+        check(lib.tg_rng_add_normal(stream_ptr(), ptr(h), ptr(out), h.numel(), float(std), seed, offset, ptr(ctr)),
+              "tg_rng_add_normal")
     return out
 
 
@@ -79,10 +91,10 @@ class DeviceNoise:
             n *= s
         return normal(tuple(shape), self.device, self.seed, self._adv(n), ctr=self.ctr)
 
-    def add_randn(self, h, std):
-        if std <= 0:
-            return h
-        return add_normal(h, std, self.seed, self._adv(h.numel()), ctr=self.ctr)
+    def add_randn(self, h, std, out=None):
+        if not torch.is_tensor(std) and std <= 0:
+            return add_normal(h, std, self.seed, 0, out=out)
+        return add_normal(h, std, self.seed, self._adv(h.numel()), ctr=self.ctr, out=out)
 
     def state(self):
         return {"seed": self.seed, "ctr": int(self.ctr.item())}

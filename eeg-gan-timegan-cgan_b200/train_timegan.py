@@ -132,6 +132,10 @@ class _DeviceNoiseAdapter:
     def randn_like(self, h, time_major: bool = False):
         return self.src.randn(h.shape)
 
+    def add_randn(self, h, std, out=None):
+        """h + std * N(0,1) as one kernel (same Philox positions as randn_like of the same shape)."""
+        return self.src.add_randn(h, std, out=out)
+
     def begin(self):
         self.src.begin()
 
@@ -163,12 +167,37 @@ def smooth_labels(size: int, smooth: float, device, noise=None) -> Tuple[torch.T
     return real, fake
 
 
-def add_instance_noise(h: torch.Tensor, std: float, noise=None, time_major: bool = False) -> torch.Tensor:
+class _AddNoise(torch.autograd.Function):
+    """h + std * N(0,1) drawn and added by one kernel; d/dh = identity, the noise is a constant (tt:46-47)."""
+
+    @staticmethod
+    def forward(ctx, h, std, src):
+        return src.add_randn(h.detach(), std)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None, None
+
+
+def add_instance_noise(h: torch.Tensor, std: float, noise=None, time_major: bool = False, out=None) -> torch.Tensor:
     """tt:46-47.  `time_major` only matters to host-replayed noise (layout of the reference's tensor).
-    `std` may be a 0-dim device tensor (CUDA-graph replay: the value changes every step, the graph does not)."""
+    `std` may be a 0-dim device tensor (CUDA-graph replay: the value changes every step, the graph does not).
+    `out` (no-grad callers only): a contiguous view that receives the result, e.g. one half of D's 2B batch."""
+    src = _noise_source(noise, h.device)
+    if hasattr(src, "add_randn"):                       # on-device Philox: draw + scale + add in one launch
+        if out is not None or not (torch.is_grad_enabled() and h.requires_grad):
+            return src.add_randn(h, std, out=out)
+        if not torch.is_tensor(std) and std <= 0:
+            return h
+        return _AddNoise.apply(h, std, src)
     if not torch.is_tensor(std) and std <= 0:
-        return h
-    return h + std * _noise_source(noise, h.device).randn_like(h, time_major)
+        res = h
+    else:
+        res = h + std * src.randn_like(h, time_major)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def _latent_is_gru_view(model) -> bool:
@@ -416,11 +445,12 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
             h_real = model.encode(x)                                                 # tt:175-176  (|| G -> S)
         h_fake = model.refine_latent(model.gen_latent(z))                            # tt:180-181 (forward only)
         fork_e.join()
-        h_real_n = add_instance_noise(h_real, inst_noise_std, nz, True)              # tt:184
-        h_fake_n = add_instance_noise(h_fake, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:185
+        # one 2B-batch pass of the D stack over [real ; fake] (tt:191-193): the noisy latents are written straight
+        # into the two halves of its input
+        h_in = torch.empty((2 * B,) + tuple(h_real.shape[1:]), dtype=torch.float32, device=h_real.device)
+        h_real_n = add_instance_noise(h_real, inst_noise_std, nz, True, out=h_in[:B])              # tt:184
+        h_fake_n = add_instance_noise(h_fake, inst_noise_std, nz, _latent_is_gru_view(model), out=h_in[B:])   # tt:185
         y_real, y_fake = smooth_labels(B, label_smooth, device, nz)                  # tt:188
-        # one 2B-batch pass of the D stack over [real ; fake] (tt:191-193)
-        h_in = torch.cat([h_real_n, h_fake_n], 0)
         masks = gru.dropout_masks(h_in)
         y_all, saves = ops.stack_forward(h_in, wd, save=True, masks=masks)
         last = y_all[:, -1, :]

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 7
+#define TG_ABI_VERSION 8
 
 #define TG_OK 0
 #define TG_ERR_ARG (-1)
@@ -159,6 +159,11 @@ int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long see
                    float hi, const unsigned long long* ctr /* NULL or device counter added to offset */);
 int tg_rng_add_normal(void* stream, const float* in /* may be NULL */, float* out, long long n, float std,
                       unsigned long long seed, unsigned long long offset, const unsigned long long* ctr);
+/* same, with the standard deviation read from device memory (one float): the instance-noise level of tt:352-353,404
+ * decays every step while a captured CUDA graph stays the same */
+int tg_rng_add_normal_dev(void* stream, const float* in /* may be NULL */, float* out, long long n,
+                          const float* std_dev, unsigned long long seed, unsigned long long offset,
+                          const unsigned long long* ctr);
 
 /* ---- data-parallel all-reduce over NVLink peer memory (net-new: the reference is single-process; replaces the
  * torch.distributed all_reduce a DDP port of train_timegan.py:141,160,220,268 would issue) ------------------
