@@ -37,6 +37,28 @@ HP = dict(label_smooth=0.2, inst_noise=0.3, clip=0.5, r1_gamma=1.0, target=0.525
 METRIC = "TimeGAN train seq/sec (T=768,C=14)"
 
 
+# stdout carries exactly ONE line (the JSON); anything a library prints on fd 1 (e.g. NCCL's version banner under
+# torchrun) is sent to stderr: fd 1 is pointed at fd 2 for the whole run and the line is written to the saved fd
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -146,7 +168,7 @@ def run_reference(a):
         "e2e": {"value": round(v, 4), "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -389,11 +411,12 @@ def run_ours(a):
     }
     if not a.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
     a = parse()
+    _guard_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

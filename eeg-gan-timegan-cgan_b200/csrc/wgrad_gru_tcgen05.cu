@@ -10,15 +10,17 @@
 // (the two cross blocks dGI[:, 2H:] y and dq x are computed and dropped: the tensor pipe is not the limit).
 // Same machinery as wgrad_tcgen05.cu: 32B-atom 128B swizzle for MN-major TF32, split-M over one CTA per SM,
 // deterministic partial reduction, fix-up warps (h_{-1} rows, bias column sums, 3xTF32 split).  The lo parts of the
-// 3xTF32 split live in TWO shared buffers (they are only needed while a stage's MMAs run), which leaves room for
+// 3xTF32 split live in THREE shared buffers (they are only needed while a stage's MMAs run), which leaves room for
 // a 6-deep ring of raw stages -- the kernel is bound by bytes in flight, not by math.
 #include "tc_common.cuh"
 #include "kernels.h"
 
 namespace {
 
-constexpr int WL_THREADS = 448;   // TMA, MMA, 4 epilogue warps, 8 fix-up warps
-constexpr int WL_FIX = 256;
+constexpr int WL_NLO = 3;                     // lo-part buffers of the 3xTF32 split: fix-up of step i waits for the MMAs of i-3
+constexpr int WL_NG = 3;                      // fix-up groups of 128 threads (chunk c belongs to group c % WL_NG)
+constexpr int WL_FIX = 128 * WL_NG;
+constexpr int WL_THREADS = 192 + WL_FIX;      // TMA, MMA, 4 epilogue warps, 4 * WL_NG fix-up warps
 constexpr int WL_TAIL = 1024;
 constexpr int WL_MAXCH = 16;   // chunks of the A operand (dGI + dq)
 
@@ -42,7 +44,7 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
   const int chunk_bytes = R * 128;
   const int stage_bytes = (GCH + ACH) * chunk_bytes;
   unsigned char* lo_base = smem + (size_t)NS * stage_bytes;                    // [2][stage_bytes] (3-pass only)
-  unsigned char* tail = lo_base + (PASSES == 3 ? 2 * (size_t)stage_bytes : 0);
+  unsigned char* tail = lo_base + (PASSES == 3 ? WL_NLO * (size_t)stage_bytes : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = bars;            // [NS] TMA -> fix-up
   uint64_t* empty = bars + NS;      // [NS] MMA -> TMA (and -> fix-up: lo buffer of two steps ago is free)
@@ -100,7 +102,7 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
         tc_fence_after();
         const uint32_t g_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t a_hi = g_hi + (uint32_t)(GCH * chunk_bytes);
-        const uint32_t g_lo = smem_u32(lo_base + (size_t)(it & 1) * stage_bytes);
+        const uint32_t g_lo = smem_u32(lo_base + (size_t)(it % WL_NLO) * stage_bytes);
         const uint32_t a_lo = g_lo + (uint32_t)(GCH * chunk_bytes);
         for (int i = 0; i < R / 8; ++i) {
           const uint32_t ko = (uint32_t)(i * 1024);
@@ -161,9 +163,10 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       }
     }
   } else {
-    // ===================== fix-up / split / column-sum warps (6..13) =====================
-    // two groups of 128 threads take the even / odd chunks of every stage; inside a group thread (u, rsub)
-    // owns the 16-byte unit u of the rows r == rsub (mod 16)
+    // ===================== fix-up / split / column-sum warps (6..) =====================
+    // WL_NG groups of 128 threads share the chunks of every stage round-robin (the fix-up is the stage of the
+    // pipeline both the producer and the MMA thread wait for); inside a group thread (u, rsub) owns the 16-byte
+    // unit u of the rows r == rsub (mod 16)
     const int t = threadIdx.x - 192;
     const int grp = t >> 7, tt = t & 127;
     const int u = tt & 7, rsub = tt >> 3;
@@ -177,12 +180,12 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
     for (int it = 0; it < steps; ++it) {
       const int s = it % NS;
       mbar_wait_bounded(&full[s], (uint32_t)((it / NS) & 1));
-      if (PASSES == 3 && it >= 2) {   // the lo buffer (it & 1) was last read by the MMAs of step it-2
-        const int j = it - 2;
+      if (PASSES == 3 && it >= WL_NLO) {   // the lo buffer (it % WL_NLO) was last read by the MMAs of step it-WL_NLO
+        const int j = it - WL_NLO;
         mbar_wait_bounded(&empty[j % NS], (uint32_t)((j / NS) & 1));
       }
       unsigned char* base = smem + (size_t)s * stage_bytes;
-      unsigned char* lo = lo_base + (size_t)(it & 1) * stage_bytes;
+      unsigned char* lo = lo_base + (size_t)(it % WL_NLO) * stage_bytes;
       for (int r = rsub; r < R; r += 16) {
         int rr = rem0 + r;
         while (rr >= p.T) rr -= p.T;
@@ -205,8 +208,8 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
           }
         };
 #pragma unroll
-        for (int cb = 0; cb < (WL_MAXCH + 8) / 2; cb += 3) {
-          const int c0 = 2 * cb + grp, c1 = c0 + 2, c2 = c0 + 4;
+        for (int cb = 0; cb < (WL_MAXCH + 8 + WL_NG - 1) / WL_NG; cb += 3) {
+          const int c0 = WL_NG * cb + grp, c1 = c0 + WL_NG, c2 = c0 + 2 * WL_NG;
           float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0;
           if (c0 < NCHK) a0 = *reinterpret_cast<const float4*>(base + (size_t)c0 * chunk_bytes + off);
           if (c1 < NCHK) a1 = *reinterpret_cast<const float4*>(base + (size_t)c1 * chunk_bytes + off);
@@ -223,13 +226,13 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
     }
     // per-CTA column-sum partial (bias gradients)
     mbar_wait_bounded(acc_full, 0);
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(WL_FIX) : "memory");
 #pragma unroll
     for (int ci = 0; ci < WL_MAXCH / 2; ++ci) {
-      const int c = 2 * ci + grp;
+      const int c = WL_NG * ci + grp;
       if (c < GCH) *reinterpret_cast<float4*>(db_red + (size_t)rsub * (GCH * 32) + c * 32 + cu * 4) = colsum[ci];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(WL_FIX) : "memory");
     float* cs = p.ws + (size_t)blockIdx.x * ((size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H + GCH * 32) +
                 (size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H;
     for (int n = t; n < GCH * 32; n += WL_FIX) {
@@ -322,13 +325,13 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
   int R = 32, nstage = 0;
   for (; R >= 8; R >>= 1) {
     const int stage_bytes = (GCH + ACH) * R * 128;
-    nstage = (tg_gemm_smem_budget() - WL_TAIL - 4 * R * 128) / stage_bytes - (passes == 3 ? 2 : 0);
+    nstage = (tg_gemm_smem_budget() - WL_TAIL - 4 * R * 128) / stage_bytes - (passes == 3 ? WL_NLO : 0);
     if (nstage >= 4) break;
   }
   if (R < 8 || nstage < 3) { tg_set_error("wgrad_gru: tile does not fit shared memory"); return TG_ERR_UNSUPPORTED; }
   if (nstage > 8) nstage = 8;
   const int stage_bytes = (GCH + ACH) * R * 128;
-  size_t smem = (size_t)(nstage + (passes == 3 ? 2 : 0)) * stage_bytes + WL_TAIL + 4 * (size_t)R * 128;
+  size_t smem = (size_t)(nstage + (passes == 3 ? WL_NLO : 0)) * stage_bytes + WL_TAIL + 4 * (size_t)R * 128;
   if (smem < (size_t)16 * GCH * 32 * 4 + WL_TAIL) smem = (size_t)16 * GCH * 32 * 4 + WL_TAIL;
 
   alignas(64) CUtensorMap tmG1, tmG2, tmA1, tmA2;
