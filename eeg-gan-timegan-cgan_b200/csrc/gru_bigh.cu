@@ -17,12 +17,12 @@ constexpr int NT = 512, NW = NT / 32, BT = 4;
 
 // out[b][row] = sum_c W[row][c] * vin[b][c]   (NV input vectors per sequence share every weight load)
 // A warp walks RU rows at a time so that the weight loads of RU rows (L2 latency ~600 clk) are in flight together.
-// (Measured: a one-item-deep software pipeline across row groups is slower, 814 vs 718 ms per c4 joint step at
-// H = 256 -- fewer loads in flight -- so the simple unroll stays.)
+// (Measured: a one-item-deep software pipeline across row groups is slower -- fewer loads in flight -- so the simple
+// unroll stays.)
 template <int NV>
 __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, int rows, int cols, const float* vin,
                                             int vin_stride, float* out, int out_stride) {
-  constexpr int RU = (NV == 1) ? 4 : 2;
+  constexpr int RU = (NV == 1) ? 8 : 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c4n = cols >> 2;
   for (int row0 = warp * RU; row0 < rows; row0 += NW * RU) {
@@ -50,15 +50,31 @@ __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, int row
             acc[u][v][b] = fmaf(w4[u].x, x4.x, fmaf(w4[u].y, x4.y, fmaf(w4[u].z, x4.z, fmaf(w4[u].w, x4.w, acc[u][v][b]))));
         }
     }
+    // RU * NV * BT == 32 partial sums per lane: a transposing butterfly (16 + 8 + 4 + 2 + 1 shuffles instead of
+    // 32 x 5) leaves the total of flat index l = (u * NV + v) * BT + b in lane l -- the shuffle unit, not L2, was
+    // the limit of this loop -- and the 32 results go out in one store instruction.
+    static_assert(RU * NV * BT == 32, "one total per lane");
+    float vals[32];
 #pragma unroll
     for (int u = 0; u < RU; ++u)
 #pragma unroll
       for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-          const float s = warp_sum(acc[u][v][b]);
-          if (lane == 0 && row0 + u < rows) out[(size_t)(v * BT + b) * out_stride + row0 + u] = s;
-        }
+        for (int b = 0; b < BT; ++b) vals[(u * NV + v) * BT + b] = acc[u][v][b];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const float send = up ? vals[i] : vals[i + o];
+        const float keep = up ? vals[i + o] : vals[i];
+        vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    {
+      const int u = lane / (NV * BT), v = (lane / BT) % NV, b = lane % BT;
+      if (row0 + u < rows) out[(size_t)(v * BT + b) * out_stride + row0 + u] = vals[0];
+    }
   }
 }
 
