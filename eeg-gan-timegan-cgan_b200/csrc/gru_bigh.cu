@@ -26,13 +26,13 @@ __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, int row
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c4n = cols >> 2;
   for (int row0 = warp * RU; row0 < rows; row0 += NW * RU) {
-    float acc[RU][NV][BT];
+    float2 acc[RU][NV][BT];          // packed FFMA2: .x sums the even columns of a float4 pair, .y the odd ones
 #pragma unroll
     for (int u = 0; u < RU; ++u)
 #pragma unroll
       for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int b = 0; b < BT; ++b) acc[u][v][b] = 0.f;
+        for (int b = 0; b < BT; ++b) acc[u][v][b] = make_float2(0.f, 0.f);
     for (int c4 = lane; c4 < c4n; c4 += 32) {
       float4 w4[RU];
 #pragma unroll
@@ -45,9 +45,12 @@ __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, int row
 #pragma unroll
         for (int b = 0; b < BT; ++b) {
           const float4 x4 = reinterpret_cast<const float4*>(vin + (size_t)(v * BT + b) * vin_stride)[c4];
+          const float2 x01 = make_float2(x4.x, x4.y), x23 = make_float2(x4.z, x4.w);
 #pragma unroll
-          for (int u = 0; u < RU; ++u)
-            acc[u][v][b] = fmaf(w4[u].x, x4.x, fmaf(w4[u].y, x4.y, fmaf(w4[u].z, x4.z, fmaf(w4[u].w, x4.w, acc[u][v][b]))));
+          for (int u = 0; u < RU; ++u) {
+            acc[u][v][b] = __ffma2_rn(make_float2(w4[u].x, w4[u].y), x01, acc[u][v][b]);
+            acc[u][v][b] = __ffma2_rn(make_float2(w4[u].z, w4[u].w), x23, acc[u][v][b]);
+          }
         }
     }
     // RU * NV * BT == 32 partial sums per lane: a transposing butterfly (16 + 8 + 4 + 2 + 1 shuffles instead of
@@ -60,7 +63,7 @@ __device__ __forceinline__ void matvec_rows(const float* __restrict__ W, int row
 #pragma unroll
       for (int v = 0; v < NV; ++v)
 #pragma unroll
-        for (int b = 0; b < BT; ++b) vals[(u * NV + v) * BT + b] = acc[u][v][b];
+        for (int b = 0; b < BT; ++b) vals[(u * NV + v) * BT + b] = acc[u][v][b].x + acc[u][v][b].y;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
       const bool up = (lane & o) != 0;
