@@ -345,8 +345,7 @@ def run_ours(a):
     else:
         prof_steps = a.steps
 
-    if tdist.peer_comm() is not None:
-        tdist.peer_comm().check_status()
+    tdist.shutdown()          # checks the peer all-reduce status word, unmaps / frees the peer regions
     if world > 1:
         td.destroy_process_group()
     if rank != 0:

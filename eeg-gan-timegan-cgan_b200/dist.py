@@ -81,6 +81,15 @@ def disable():
     _GROUP, _ENABLED, _COMM_STREAM = None, False, None
 
 
+def shutdown():
+    """Collective teardown of the peer-memory communicator (before destroy_process_group)."""
+    global _PEER
+    if _PEER is not None:
+        _PEER.check_status()
+        _PEER.close()
+        _PEER = None
+
+
 def is_enabled() -> bool:
     return _ENABLED
 
@@ -225,6 +234,22 @@ class PeerComm:
         """Raises if a kernel gave up waiting for a peer (synchronises)."""
         if int(self.status.item()) != 0:
             raise RuntimeError("peer all-reduce timed out waiting for another rank")
+
+    def close(self):
+        """Unmap the peers' regions and free this rank's (collective: every rank must call it; no all-reduce may be
+        in flight).  Safe to call twice."""
+        if self.regions is None:
+            return
+        torch.cuda.synchronize(self.device)
+        td.barrier(group=self.group)          # nobody is still reading this rank's staging areas
+        with torch.cuda.device(self.device):
+            for r in range(self.world):
+                if r != self.rank and self.regions[r]:
+                    self._check(self._lib.tg_peer_close(self.regions[r]), "tg_peer_close")
+            td.barrier(group=self.group)      # every mapping of this rank's region is gone
+            self._check(self._lib.tg_peer_free(self._own), "tg_peer_free")
+        self.regions = None
+        self.sites.clear()
 
 
 class GradBuckets:

@@ -62,6 +62,7 @@ def main():
         and dw < 2e-5 and same
     print(f"rank {rank}: graph vs eager DP: max loss diff {dl:.2e}, max weight diff {dw:.2e}, "
           f"weights identical across ranks: {same} -> {'OK' if ok else 'MISMATCH'}", flush=True)
+    D.shutdown()
     td.destroy_process_group()
     sys.exit(0 if ok else 1)
 

@@ -96,6 +96,7 @@ def main():
     pc.check_status()
     print(f"rank {rank}: {'OK' if ok else 'MISMATCH'}  1.16 MB bucket: peer kernel {t_peer*1e3:.1f} us, NCCL {t_nccl*1e3:.1f} us",
           flush=True)
+    D.shutdown()
     td.destroy_process_group()
     sys.exit(0 if ok else 1)
 
