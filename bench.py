@@ -345,6 +345,8 @@ def run_ours(a):
     else:
         prof_steps = a.steps
 
+    comm_name = (None if world == 1 else "peer-memory all-reduce kernels over NVLink (csrc/peer_allreduce.cu)"
+                 if tdist.peer_comm() is not None else "NCCL all_reduce")
     tdist.shutdown()          # checks the peer all-reduce status word, unmaps / frees the peer regions
     if world > 1:
         td.destroy_process_group()
@@ -386,8 +388,7 @@ def run_ours(a):
                 "ms_per_step": round(ms_e2e / a.steps, 3)},
         "gpu_launches": int(round(launches_per_step * a.steps)),
         "issue": "cuda-graph replay (1 graph launch per step)" if use_graph else "eager",
-        "comm": (None if world == 1 else "peer-memory all-reduce kernels over NVLink (csrc/peer_allreduce.cu)"
-                 if tdist.peer_comm() is not None else "NCCL all_reduce"),
+        "comm": comm_name,
         "host_issue_ms_per_step": round(host_issue_ms / a.steps, 3),
         "clocks": clk,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": round(ach_gbs, 1), "peak": hbm_peak, "unit": "GB/s",
