@@ -73,7 +73,6 @@ def parse():
     ap.add_argument("--serial", action="store_true", help="disable side-stream concurrency inside the step")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dp-graph", action="store_true", help="experimental: capture the NCCL all-reduces too (N > 1)")
-    ap.add_argument("--cpu-sample-t", type=int, default=96, help="timesteps of the CPU baseline's bounded sample")
     ap.add_argument("--wgrad-ctas", type=int, default=-1,
                     help="SMs given to the side-stream weight-gradient kernels (0 = in line; -1 = package default)")
     ap.add_argument("--bt", type=int, default=0, choices=[0, 1, 2, 4],
@@ -88,83 +87,104 @@ def workload_name(a):
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU leg: oracle port of the reference on the host cores (bounded sample)
+# CPU leg: oracle port of the reference on the host cores -- FULL-LENGTH (T = 768) joint steps, no extrapolation
 # ------------------------------------------------------------------------------------------------
-def cpu_joint_steps(a, steps, warmup, threads):
-    """Times `steps` joint steps of the oracle port on a (B, t_s, 14) sample and rescales to T=768.
+class CpuArm:
+    """The reference's joint step (tt:379-395 -> disc_step + gen_step) as restated by oracle/timegan_ref.py, on the
+    host cores.  One model / optimiser pair lives for the whole arm, like a training run."""
 
-    The sample keeps the FULL batch (per-sequence CPU cost depends on B through ATen dispatch amortisation) and
-    shortens the window to t_s timesteps; the recurrence costs the same per timestep, so a T=768 step costs
-    768/t_s times the sample (the T-independent parts -- optimiser, head -- are <1 % of a CPU step)."""
+    def __init__(self, a, threads):
+        import torch
+        from oracle import timegan_ref as R
+        self.R, self.a = R, a
+        torch.set_num_threads(threads)
+        torch.manual_seed(0)
+        self.model = R.build_model(X_DIM, a.hidden, a.hidden, a.layers, 0.0)
+        self.opts = R.make_optimizers(self.model, HP["lr_g"], HP["lr_d"], HP["betas"])
+        self.nz = R.TorchNoise()
+        self.threads = threads
+
+    def step(self, x):
+        R = self.R
+        t0 = time.perf_counter()
+        R.d_step(self.model, x, self.opts["D"], self.nz, HP["label_smooth"], HP["inst_noise"], HP["clip"],
+                 HP["r1_gamma"], HP["target"], HP["band"])
+        R.g_step(self.model, x, self.opts["G"], self.nz, HP["alpha_sup"], HP["beta_rec"], HP["inst_noise"], HP["clip"],
+                 HP["gamma_cov"], HP["gamma_acf"], HP["acf_max_lag"])
+        return time.perf_counter() - t0
+
+
+def pick_cpu_threads(a):
+    """Fastest thread count of {1, 8, all} on this host, from one short (T = 96) probe step each -- the probes only
+    choose the thread count, they are never part of a reported number."""
     import torch
-    from oracle import timegan_ref as R
-    torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    ts = min(a.cpu_sample_t, T_LEN)
-    model = R.build_model(X_DIM, a.hidden, a.hidden, a.layers, 0.0)
-    opts = R.make_optimizers(model, HP["lr_g"], HP["lr_d"], HP["betas"])
-    x = torch.rand(a.batch, ts, X_DIM)
-    nz = R.TorchNoise()
+    cores = os.cpu_count() or 1
+    probe = {}
+    for th in sorted({1, min(cores, 8), cores}):
+        arm = CpuArm(a, th)
+        x = torch.rand(a.batch, 96, X_DIM)
+        arm.step(x)
+        probe[th] = round(arm.step(x), 3)
+    return min(probe, key=probe.get), probe, cores
+
+
+def cpu_full_steps(a, steps, warmup, threads):
+    """`warmup` untimed + `steps` timed joint steps on (B, 768, 14) batches.  Returns the list of step times (s)."""
+    import torch
+    arm = CpuArm(a, threads)
+    g = torch.Generator().manual_seed(1234)
+    xs = [torch.rand(a.batch, T_LEN, X_DIM, generator=g) for _ in range(2)]
     times = []
     for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        R.d_step(model, x, opts["D"], nz, HP["label_smooth"], HP["inst_noise"], HP["clip"], HP["r1_gamma"],
-                 HP["target"], HP["band"])
-        R.g_step(model, x, opts["G"], nz, HP["alpha_sup"], HP["beta_rec"], HP["inst_noise"], HP["clip"],
-                 HP["gamma_cov"], HP["gamma_acf"], HP["acf_max_lag"])
-        dt = time.perf_counter() - t0
+        dt = arm.step(xs[i % 2])
         if i >= warmup:
             times.append(dt)
-    scale = T_LEN / ts
-    per_step = sum(times) / len(times) * scale
-    return a.batch / per_step, per_step, ts
+    return times
 
 
 def cpu_baseline(a):
     import torch
-    cores = os.cpu_count() or 1
-    best = None
-    for th in sorted({1, min(cores, 8), cores}):
-        try:
-            v, per_step, ts = cpu_joint_steps(a, 1, 0, th)
-        except Exception as e:  # pragma: no cover
-            print(f"[bench] cpu baseline with {th} threads failed: {e}", file=sys.stderr)
-            continue
-        if best is None or v > best[0]:
-            best = (v, th, per_step, ts)
-    v, th, per_step, ts = best
-    return {"value": round(v, 4), "unit": "seq/s", "cores": th, "kind": "port", "host_cores": cores,
-            "sample": f"1 joint step of oracle/timegan_ref.py (torch {torch.__version__}, CPU) on the full batch "
-                      f"{a.batch} x first {ts} of {T_LEN} timesteps, time scaled x{T_LEN / ts:g} "
-                      f"(recurrence is linear in T); best of {{1, 8, all}} threads",
-            "s_per_step_full_T": round(per_step, 3)}
+    th, probe, cores = pick_cpu_threads(a)
+    times = cpu_full_steps(a, 2, 1, th)
+    per_step = sum(times) / len(times)
+    return {"value": round(a.batch / per_step, 4), "unit": "seq/s", "cores": th, "kind": "port", "host_cores": cores,
+            "sample": f"2 timed (after 1 warm-up) full-length joint steps of oracle/timegan_ref.py (torch "
+                      f"{torch.__version__}, CPU) on {a.batch} x {T_LEN} x {X_DIM} batches -- the bench workload, no "
+                      f"rescaling; thread count chosen from T=96 probe steps {probe} (s/step)",
+            "s_per_step": round(per_step, 3)}
+
+
+def bench_config(a, world):
+    """`config` of the JSON line -- identical in both arms (the driver compares them)."""
+    return {"workload": workload_name(a), "global_batch": a.batch * world, "parallelism": f"dp{world}",
+            "l2": "8 rotating input batches; each step streams >2 GB of activations (>> 126 MB L2)"}
 
 
 def run_reference(a):
+    """--impl reference: K timed + W warm-up FULL joint steps (B x 768 x 14) of the CPU restatement of the reference.
+    Under torchrun only rank 0 works.  At N > 1 the arm's config is the same weak-scaling workload (global batch
+    B*N); the host processes it one rank-share (B sequences, full T) per step -- CPU seq/s does not depend on how many
+    shares follow, and a 2048-sequence step would take 25 x 90 s -- and says so in `sample`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    # pick the thread count that is fastest on this host from one un-timed probe each
-    probe = {}
-    for th in sorted({1, min(cores, 8), cores}):
-        probe[th] = cpu_joint_steps(a, 1, 0, th)[0]
-    th = max(probe, key=probe.get)
-    steps = max(1, a.steps)
-    # size the sample so that `steps` timed CPU steps take about 150 s on this host
-    sample_s = a.batch / probe[th] * a.cpu_sample_t / T_LEN       # seconds per sampled step at cpu_sample_t
-    if steps * sample_s > 150.0:
-        a.cpu_sample_t = max(16, int(a.cpu_sample_t * 150.0 / (steps * sample_s)) // 8 * 8)
-    v, per_step, ts = cpu_joint_steps(a, steps, min(a.warmup, 1), th)
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
+    th, probe, cores = pick_cpu_threads(a)
+    steps, warmup = max(1, a.steps), max(0, a.warmup)
+    times = cpu_full_steps(a, steps, warmup, th)
+    per_step = sum(times) / len(times)
+    v = a.batch / per_step
+    share = "" if world == 1 else (f"; each step is one rank's share ({a.batch} of the {a.batch * world} sequences of "
+                                   f"the global batch), seq/s is per host and independent of the number of shares")
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": "seq/s", "n_gpus": a.gpus, "steps": steps,
-        "warmup": a.warmup, "ms_per_step": round(per_step * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "warmup": warmup, "ms_per_step": round(per_step * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "device": "host CPU"},
+        "config": bench_config(a, world),
         "cpu_baseline": {"value": round(v, 4), "unit": "seq/s", "cores": th, "kind": "port", "host_cores": cores,
-                         "sample": f"each step = 1 joint step of oracle/timegan_ref.py on the full batch {a.batch} x "
-                                   f"first {ts} of {T_LEN} timesteps, time scaled x{T_LEN / ts:g}; thread count "
-                                   f"chosen from probes {probe}"},
+                         "sample": f"every step = 1 full-length joint step of oracle/timegan_ref.py on a {a.batch} x "
+                                   f"{T_LEN} x {X_DIM} batch (no time truncation, no rescaling){share}; thread count "
+                                   f"chosen from T=96 probe steps {probe} (s/step)"},
         "e2e": {"value": round(v, 4), "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -381,8 +401,7 @@ def run_ours(a):
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if a.proj == "fp32" else "fp32 (bf16 projections)",
         "data": "synthetic",
-        "config": {"workload": workload_name(a), "global_batch": B * world, "parallelism": f"dp{world}",
-                   "l2": f"{n_batches} rotating input batches; each step streams >2 GB of activations (>> 126 MB L2)"},
+        "config": bench_config(a, world),
         "e2e": {"value": round(seqs / (ms_e2e * 1e-3), 2), "unit": "seq/s",
                 "h2d_bytes_per_step": B * T_LEN * X_DIM * 4, "d2h_bytes_per_step": 8 * 4,
                 "ms_per_step": round(ms_e2e / a.steps, 3)},

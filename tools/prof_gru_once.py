@@ -5,6 +5,8 @@ import timegan_b200
 from timegan_b200 import ops
 dev = 'cuda'
 B, T, H = (int(sys.argv[1]) if len(sys.argv) > 1 else 256), 768, (int(sys.argv[2]) if len(sys.argv) > 2 else 64)
+BT = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+ops.set_bt_override(BT)
 torch.manual_seed(0)
 w = []
 for l in range(3):
