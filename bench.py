@@ -14,9 +14,11 @@ One JSON line on rank 0:
                D2H read of the 8 logged loss scalars, all inside the timed region
   roofline     dominant kernel family of the step (device time share), its algorithmic bytes / launch duration
                against the measured HBM copy bandwidth; `ffma` gives the same family against the fp32 FMA peak
-  cpu_baseline oracle/timegan_ref.py (the CPU restatement of the reference; kind "port") on this box's host cores,
-               on a bounded sample of the same workload
-  --impl reference : only the CPU leg, K timed steps of that bounded sample (rank 0 only under torchrun).
+  cpu_baseline oracle/timegan_ref.py (the CPU restatement of the reference; kind "port") on this box's host cores:
+               2 timed FULL-LENGTH joint steps of the same workload (B x 768 x 14; no truncation, no rescaling)
+  also.c3      BASELINE config c3 (h = 128, reduced-precision projections) measured the same way in the same run
+  dp_check     (N > 1) every replica holds bit-identical weights after all steps of the run
+  --impl reference : only the CPU leg, K timed + W warm-up full-length steps (rank 0 only under torchrun).
 """
 import argparse
 import json
@@ -70,6 +72,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
     ap.add_argument("--proj", type=str, default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also-c3", dest="also_c3", action="store_false",
+                    help="skip the secondary BASELINE config c3 (h=128, reduced-precision projections) line under `also`")
     ap.add_argument("--serial", action="store_true", help="disable side-stream concurrency inside the step")
     ap.add_argument("--no-graph", action="store_true", help="issue every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--dp-graph", action="store_true", help="experimental: capture the NCCL all-reduces too (N > 1)")
@@ -234,6 +238,69 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # GPU leg
 # ------------------------------------------------------------------------------------------------
+def secondary_config(a, dev, world, rank, hidden, proj, label, steps=6, warmup=3):
+    """Device-resident joint-step throughput of ANOTHER BASELINE.json configuration inside the same run (same
+    timing rules: warm-up, barrier + synchronize on both sides, CUDA events, max over ranks).  Reported under
+    `also` -- the headline `value` stays the c2 workload at every N so that the driver's scaling efficiency
+    compares like with like."""
+    import torch
+    import torch.distributed as td
+    import timegan_b200 as tg
+    from timegan_b200 import ops, dist as tdist, train_timegan as tt
+    old = ops.get_proj_mode()
+    ops.set_proj_mode(proj)
+    try:
+        torch.manual_seed(43)
+        model = tg.TimeGAN(X_DIM, hidden, hidden, a.layers, 0.0).to(dev)
+        use_graph = (not a.no_graph) and (world == 1 or tdist.peer_comm() is not None)
+        optD = tg.FusedAdam(model.discriminator.parameters(), lr=HP["lr_d"], betas=HP["betas"], capturable=use_graph)
+        optG = tg.FusedAdam(tt._params(model.generator, model.supervisor, model.embedder, model.recovery),
+                            lr=HP["lr_g"], betas=HP["betas"], capturable=use_graph)
+        g = torch.Generator().manual_seed(4321 + rank)
+        xs = [torch.rand(a.batch, T_LEN, X_DIM, generator=g).to(dev) for _ in range(4)]
+        if use_graph:
+            step = tt.GraphedJointStep(model, optD, optG, dev, label_smooth=HP["label_smooth"], clip=HP["clip"],
+                                       r1_gamma=HP["r1_gamma"], target_acc=HP["target"], band=HP["band"],
+                                       alpha_sup=HP["alpha_sup"], beta_rec=HP["beta_rec"], gamma_cov=HP["gamma_cov"],
+                                       gamma_acf=HP["gamma_acf"], acf_max_lag=HP["acf_max_lag"], warmup=2)
+            joint = lambda x: step(x, HP["inst_noise"])
+        else:
+            def joint(x):
+                d = tt.disc_step(model, x, dev, optD, HP["label_smooth"], HP["inst_noise"], HP["clip"], None,
+                                 HP["r1_gamma"], target_acc=HP["target"], band=HP["band"], sync=False)
+                q = tt.gen_step(model, x, dev, optG, HP["alpha_sup"], HP["beta_rec"], HP["inst_noise"], HP["clip"],
+                                None, HP["gamma_cov"], HP["gamma_acf"], HP["acf_max_lag"], sync=False)
+                return torch.stack([v.float().reshape(()) for v in d + q])
+
+        def barrier():
+            if world > 1:
+                td.barrier()
+            torch.cuda.synchronize()
+        for i in range(warmup + (1 if use_graph else 0)):
+            joint(xs[i % 4])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            out = joint(xs[i % 4])
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+            ms = float(t.item())
+        ok = bool(torch.isfinite(out).all().item())
+        del model, optD, optG, xs
+        torch.cuda.empty_cache()
+        return {"workload": f"{label}: TimeGAN joint step z=h={hidden} L={a.layers} B={a.batch}/GPU T={T_LEN} C={X_DIM} "
+                            f"{proj} projections", "global_batch": a.batch * world, "value": round(a.batch * world * steps / (ms * 1e-3), 2),
+                "unit": "seq/s", "ms_per_step": round(ms / steps, 3), "steps": steps, "warmup": warmup,
+                "issue": "cuda-graph replay" if use_graph else "eager", "finite": ok}
+    finally:
+        ops.set_proj_mode(old)
+
+
 def run_ours(a):
     import torch
     import torch.distributed as td
@@ -365,6 +432,23 @@ def run_ours(a):
     else:
         prof_steps = a.steps
 
+    # ---- data-parallel self-check: after all these optimiser steps every replica must hold bit-identical weights
+    #      (each rank saw DIFFERENT data; only a correct gradient / statistics all-reduce keeps them in lock step) ----
+    dp_check = None
+    if world > 1:
+        fp = torch.stack([p.detach().double().sum() for p in model.parameters()])
+        lo, hi = fp.clone(), fp.clone()
+        td.all_reduce(lo, op=td.ReduceOp.MIN)
+        td.all_reduce(hi, op=td.ReduceOp.MAX)
+        dp_check = {"replicas_bit_identical": bool(torch.equal(lo, hi)),
+                    "max_abs_param_sum_spread": float((hi - lo).abs().max().item()),
+                    "steps_checked": int(max(a.warmup, 3) + 2 * a.steps + 6)}
+    also = {}
+    if a.also_c3 and workload_name(a).startswith("c2"):
+        del graphed
+        torch.cuda.empty_cache()
+        also["c3"] = secondary_config(a, dev, world, rank, 128, "bf16", "c3")
+
     comm_name = (None if world == 1 else "peer-memory all-reduce kernels over NVLink (csrc/peer_allreduce.cu)"
                  if tdist.peer_comm() is not None else "NCCL all_reduce")
     tdist.shutdown()          # checks the peer all-reduce status word, unmaps / frees the peer regions
@@ -428,6 +512,10 @@ def run_ours(a):
                          "TFLOPs": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 else 0.0}
                      for k, v in prof.items() if v["calls"]},
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
+    if also:
+        line["also"] = also
     if not a.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline(a)
     emit(line)

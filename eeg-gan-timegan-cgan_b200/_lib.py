@@ -64,6 +64,7 @@ SIGNATURES = {
     "tg_sumsq": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_ll), _vp, _vp, _sz]),
     "tg_adam": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _vp,
                      _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "tg_snapshot_if_better": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _vp, _vp, _vp, _f]),
     "tg_rng_uniform": (_i, [_vp, _vp, _ll, _ull, _ull, _f, _f, _vp]),
     "tg_rng_add_normal": (_i, [_vp, _vp, _vp, _ll, _f, _ull, _ull, _vp]),
     "tg_rng_add_normal_dev": (_i, [_vp, _vp, _vp, _ll, _vp, _ull, _ull, _vp]),

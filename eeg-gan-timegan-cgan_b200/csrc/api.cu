@@ -126,6 +126,19 @@ int tg_long_chunks() {
 static std::atomic<int> g_wgrad_cta_cap{0};
 int tg_wgrad_cta_cap() { return g_wgrad_cta_cap.load(std::memory_order_relaxed); }
 
+// how long a peer all-reduce CTA waits for another rank before it reports failure (TIMEGAN_B200_PEER_TIMEOUT_MS,
+// tg_set_option("peer_timeout_ms")): long enough for a rank that is busy writing a checkpoint or collecting garbage
+static std::atomic<int> g_peer_timeout_ms{-1};
+int tg_peer_timeout_ms() {
+  int x = g_peer_timeout_ms.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_PEER_TIMEOUT_MS");
+    x = (e && atoi(e) > 0) ? atoi(e) : 10000;
+    g_peer_timeout_ms.store(x);
+  }
+  return x;
+}
+
 size_t tg_sumsq_ws_bytes(int n, const long long* sizes);
 
 extern "C" {
@@ -135,6 +148,7 @@ const char* tg_last_error(void) { return g_err; }
 int tg_device_sm_count(void) { return tg_num_sms(); }
 int tg_set_option(const char* key, int value) {
   if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
+  if (key && strcmp(key, "peer_timeout_ms") == 0) { g_peer_timeout_ms.store(value < 1 ? 1 : value); return TG_OK; }
   tg_set_error("set_option: unknown key '%s'", key ? key : "(null)");
   return TG_ERR_ARG;
 }
@@ -326,6 +340,12 @@ int tg_adam(void* stream, int n, float* const* params, const float* const* grads
   ProfScope _ps(stream, K_OPTIM, 0.0, 0.0);
   return tg_adam_multi_impl((cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, sizes, sumsq, max_norm, lr,
                             beta1, beta2, eps, step, grad_scale, dev_state);
+}
+
+int tg_snapshot_if_better(void* stream, int n, float* const* dst, const float* const* src, const long long* sizes,
+                          const float* value, float* best, float* best_step, float step) {
+  ProfScope _ps(stream, K_OPTIM, 0.0, 0.0);
+  return tg_snapshot_if_better_impl((cudaStream_t)stream, n, dst, src, sizes, value, best, best_step, step);
 }
 
 int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,

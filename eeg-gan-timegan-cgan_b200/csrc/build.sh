@@ -16,5 +16,6 @@ for s in "${SRCS[@]}"; do
   fi
 done
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
-"$NVCC" -shared -o "$OUT" $(printf "$HERE/build/%s.o " "${SRCS[@]}") -lcudart_static -ldl -lrt -lpthread
+# the shared CUDA runtime (the one torch has already loaded): the library then carries no copy of libcudart
+"$NVCC" -shared -o "$OUT" $(printf "$HERE/build/%s.o " "${SRCS[@]}") --cudart shared -ldl -lrt -lpthread
 echo "built $OUT"

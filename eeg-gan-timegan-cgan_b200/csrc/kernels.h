@@ -60,6 +60,7 @@ int tg_max_optin_smem();
 int tg_gemm_smem_budget();
 int tg_long_chunks();
 int tg_wgrad_cta_cap();
+int tg_peer_timeout_ms();
 
 // column sums out[N] (+)= sum_m X[m*ld + n]; ws >= tg_colsum_ws_bytes(N)
 size_t tg_colsum_ws_bytes(int N);

@@ -29,6 +29,8 @@ int tg_sumsq_multi_impl(cudaStream_t st, int n, const float* const* grads, const
 int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float* const* grads, float* const* exp_avg,
                        float* const* exp_avg_sq, const long long* sizes, const float* sumsq, float max_norm, float lr,
                        float beta1, float beta2, float eps, int step, float grad_scale, float* dev_state);
+int tg_snapshot_if_better_impl(cudaStream_t st, int n, float* const* dst, const float* const* src,
+                               const long long* sizes, const float* value, float* best, float* best_step, float step);
 
 // rng
 int tg_rng_uniform_impl(cudaStream_t st, float* out, long long n, unsigned long long seed, unsigned long long offset,

@@ -109,6 +109,27 @@ __global__ void __launch_bounds__(MT_THREADS) adam_multi_kernel(const __grid_con
   }
 }
 
+// Best-checkpoint snapshot without a host round trip (train_timegan.py:410-413: "if g_total < best: save"):
+// every block reads the candidate loss and the best-so-far from device memory and copies its chunk of the
+// weights / optimiser state into the snapshot only when the step improved; a one-thread kernel launched after
+// it commits the new best and the step number.  m[] / v[] of MtArgs are unused here.
+__global__ void __launch_bounds__(MT_THREADS) snapshot_if_better_kernel(const __grid_constant__ MtArgs a,
+                                                                        const float* __restrict__ value,
+                                                                        const float* __restrict__ best) {
+  if (!(value[0] < best[0])) return;
+  const int t = find_tensor(a, blockIdx.x);
+  const long long base = (long long)(blockIdx.x - a.blk_start[t]) * MT_CHUNK;
+  const long long end = min(a.size[t], base + MT_CHUNK);
+  float* dst = a.p[t];
+  const float* src = a.g[t];
+  for (long long i = base + threadIdx.x; i < end; i += MT_THREADS) dst[i] = src[i];
+}
+
+__global__ void snapshot_commit_kernel(const float* __restrict__ value, float* __restrict__ best,
+                                       float* __restrict__ best_step, float step) {
+  if (value[0] < best[0]) { best[0] = value[0]; best_step[0] = step; }
+}
+
 int fill_blocks(MtArgs& a, const long long* sizes, int n) {
   int blk = 0;
   for (int i = 0; i < n; ++i) {
@@ -189,4 +210,25 @@ int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float
     if (rc) return rc;
   }
   return TG_OK;
+}
+
+int tg_snapshot_if_better_impl(cudaStream_t st, int n, float* const* dst, const float* const* src,
+                               const long long* sizes, const float* value, float* best, float* best_step, float step) {
+  TG_REQUIRE(n >= 0 && value && best && best_step && (n == 0 || (dst && src && sizes)), TG_ERR_ARG,
+             "snapshot_if_better: bad arguments");
+  for (int i0 = 0; i0 < n; i0 += TG_MT_MAX) {
+    const int cnt = (n - i0 < TG_MT_MAX) ? n - i0 : TG_MT_MAX;
+    MtArgs a{};
+    for (int i = 0; i < cnt; ++i) {
+      TG_REQUIRE(dst[i0 + i] && src[i0 + i] && sizes[i0 + i] > 0, TG_ERR_ARG, "snapshot_if_better: tensor %d null/empty",
+                 i0 + i);
+      a.p[i] = dst[i0 + i]; a.g[i] = src[i0 + i];
+    }
+    const int blocks = fill_blocks(a, sizes + i0, cnt);
+    snapshot_if_better_kernel<<<blocks, MT_THREADS, 0, st>>>(a, value, best);
+    int rc = tg_check_launch("snapshot_if_better");
+    if (rc) return rc;
+  }
+  snapshot_commit_kernel<<<1, 1, 0, st>>>(value, best, best_step, step);
+  return tg_check_launch("snapshot_commit");
 }

@@ -17,7 +17,10 @@
 //   * the epoch of a call site lives in device memory and is advanced by the last CTA of each launch, so a
 //     replayed graph keeps counting.  Staging is double-buffered by epoch parity: a rank can only overwrite
 //     parity p again after every peer has signalled the epoch in between, i.e. has finished reading p.
-// A spin that exceeds ~2 s (a peer died) sets *status and gives up instead of hanging the GPU.
+// A spin that exceeds the timeout (default 10 s, tg_set_option("peer_timeout_ms")) means a peer is gone: the kernel
+// sets *status and POISONS its output chunk with NaN instead of summing stale staging data -- the step's losses
+// and weights turn non-finite at once and dist.PeerComm.check_status() (polled by the training loop at every
+// flush / checkpoint) raises, rather than the replicas silently drifting apart.
 #include "../../include/timegan_b200.h"
 #include "common.cuh"
 #include "kernels.h"
@@ -39,6 +42,7 @@ struct PeerArgs {
   unsigned int* epoch;               // local {epoch, finished-CTA counter}
   unsigned int* status;              // local error word (0 = ok)
   int rank, world, nchunks;
+  long long timeout_clk;
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -86,13 +90,17 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
   __syncthreads();
 
   // 2. publish to every peer, then wait for every peer's chunk c
+  __shared__ int failed;
+  if (tid == 0) failed = 0;
+  __syncthreads();
   if (tid < a.world && tid != a.rank) {
     st_release_sys(a.flags[tid] + (size_t)c * a.world + a.rank, e);
     const unsigned int* f = a.flags[a.rank] + (size_t)c * a.world + tid;
     const long long t0 = clock64();
     while ((int)(ld_acquire_sys(f) - e) < 0) {
-      if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer is gone; report instead of hanging the device
+      if (clock64() - t0 > a.timeout_clk) {  // a peer is gone; report instead of hanging the device
         atomicExch(a.status, 1u);
+        failed = 1;
         break;
       }
       __nanosleep(64);
@@ -100,8 +108,12 @@ __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid
   }
   __syncthreads();
 
-  // 3. pull and add in rank order (identical on every rank => bit-identical results everywhere)
-  if (vec) {
+  // 3. pull and add in rank order (identical on every rank => bit-identical results everywhere); after a timeout
+  //    the staging slots of the missing peer hold the data of two epochs ago -- never sum those
+  if (failed) {
+    const float nan = __int_as_float(0x7fc00000);
+    for (int i = tid; i < len; i += PR_THREADS) tens[i] = nan;
+  } else if (vec) {
     for (int i = tid * 4; i < len; i += PR_THREADS * 4) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int r = 0; r < a.world; ++r) {
@@ -212,6 +224,7 @@ int tg_peer_allreduce(void* stream, int rank, int world, void* const* regions, s
   a.epoch = epoch;
   a.status = status;
   a.rank = rank; a.world = world; a.nchunks = blk;
+  a.timeout_clk = (long long)tg_peer_timeout_ms() * 2000000LL;      // ~2 GHz SM clock
   peer_allreduce_kernel<<<blk, PR_THREADS, 0, (cudaStream_t)stream>>>(a);
   return tg_check_launch("peer_allreduce");
 }

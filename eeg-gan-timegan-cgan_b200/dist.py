@@ -24,16 +24,32 @@ _COMM_STREAM = None    # side stream for gradient buckets
 _PEER = None           # PeerComm: all-reduce kernels over NVLink peer memory (CUDA ranks of one box)
 
 
+def local_device() -> Optional[torch.device]:
+    """The GPU of this rank: cuda:LOCAL_RANK (torchrun's convention, one process per GPU).  Makes it the current
+    device, so that `device_autoselect()` and every allocation that follows land on it -- without this every rank
+    of `torchrun -m timegan_b200.train_timegan` would sit on cuda:0."""
+    if not torch.cuda.is_available():
+        return None
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if local >= torch.cuda.device_count():
+        raise RuntimeError(f"LOCAL_RANK={local} but only {torch.cuda.device_count()} CUDA device(s) are visible")
+    torch.cuda.set_device(local)
+    return torch.device("cuda", local)
+
+
 def init(backend: Optional[str] = None, device: Optional[torch.device] = None):
-    """Initialise from torchrun's environment (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*). Returns (rank, world)."""
+    """Initialise from torchrun's environment (RANK/LOCAL_RANK/WORLD_SIZE/MASTER_*). Returns (rank, world).
+    `device=None` under torchrun selects (and makes current) cuda:LOCAL_RANK."""
     global _GROUP, _ENABLED
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         _ENABLED = False
         return 0, 1
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if device is None and backend == "nccl":
+        device = local_device()
     if not td.is_initialized():
-        if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
         kw = {}
         if backend == "nccl" and device is not None:
             kw["device_id"] = device
@@ -77,8 +93,8 @@ def enable(group=None):
 
 def disable():
     """Back to single-process behaviour.  The peer region (if any) stays mapped; enable() re-activates it."""
-    global _GROUP, _ENABLED, _COMM_STREAM
-    _GROUP, _ENABLED, _COMM_STREAM = None, False, None
+    global _GROUP, _ENABLED, _COMM_STREAM, _SHARD
+    _GROUP, _ENABLED, _COMM_STREAM, _SHARD = None, False, None, None
 
 
 def shutdown():
@@ -102,12 +118,27 @@ def rank() -> int:
     return td.get_rank(_GROUP) if _ENABLED else 0
 
 
+_SHARD = None          # (sequences on this rank, sequences in the global batch) of the batch in flight, or None
+
+
+def global_count(count) -> float:
+    """Global-batch size of a quantity whose LOCAL size is `count` (sequences, rows, elements: anything
+    proportional to the number of sequences).  Every rank sees the global batch before it is sharded
+    (`shard_batch`), so the ratio global / local is known on the host without a synchronisation -- also for the
+    ragged last batch of an epoch (drop_last=False, tt:33-37), where the ranks hold shards of different sizes."""
+    if not _ENABLED:
+        return float(count)
+    if _SHARD is not None:
+        return float(count) * _SHARD[1] / _SHARD[0]
+    return float(count) * world_size()
+
+
 def allreduce_stats(t: torch.Tensor, count) -> Tuple[torch.Tensor, float]:
     """SUM-all-reduce a small statistics tensor together with its sample count.
 
-    Returns (reduced tensor, global count).  Single process: identity.  Shards are equal-sized by
-    construction (`shard_batch` refuses ragged splits), so the global count is world * count and no host
-    synchronisation is needed to learn it.
+    Returns (reduced tensor, global count).  Single process: identity.  Sums are count-weighted by construction
+    (every rank adds the statistics of the sequences it holds), and the global count follows from the shard
+    bookkeeping of `shard_batch` (`global_count`), so ragged shards need no extra collective.
     """
     if not _ENABLED:
         return t, float(count)
@@ -116,7 +147,7 @@ def allreduce_stats(t: torch.Tensor, count) -> Tuple[torch.Tensor, float]:
         _PEER.allreduce_([buf])
     else:
         td.all_reduce(buf, op=td.ReduceOp.SUM, group=_GROUP)
-    return buf, float(count) * world_size()
+    return buf, global_count(count)
 
 
 class _GlobalMean(torch.autograd.Function):
@@ -371,23 +402,34 @@ class GradReducer:
         self.handles = []
 
 
-_WARNED_RAGGED = False
+def shard_bounds(n: int, w: int, r: int) -> Tuple[int, int]:
+    """[start, end) of rank r's contiguous shard of n sequences over w ranks: the first n % w ranks hold one more."""
+    per, extra = divmod(n, w)
+    start = r * per + min(r, extra)
+    return start, start + per + (1 if r < extra else 0)
 
 
-def shard_batch(x: torch.Tensor) -> torch.Tensor:
-    """Contiguous shard of a global batch for this rank.  Every rank must hold the same number of sequences
-    (allreduce_stats relies on it), so a ragged tail (n % world != 0, e.g. the last batch of an epoch with
-    drop_last=False, tt:33-37) is trimmed to the largest multiple of the world size."""
-    global _WARNED_RAGGED
+def shard_batch(x: torch.Tensor) -> Optional[torch.Tensor]:
+    """Contiguous shard of a global batch for this rank.  Every sequence of the batch is used, like the
+    reference's single process does with drop_last=False (tt:33-37): a ragged batch (n % world != 0) gives the
+    first n % world ranks one sequence more, and the loss / gradient conventions stay exact because every
+    statistic is a count-weighted sum over the global count (`global_count`).  A batch with fewer sequences
+    than ranks returns None on EVERY rank (all ranks see the same n): the callers skip it -- a rank without a
+    single sequence cannot take part in the step's kernels."""
+    global _SHARD
     if not _ENABLED:
         return x
     w, r = world_size(), rank()
     n = x.shape[0]
     if n < w:
-        raise ValueError(f"global batch {n} is smaller than the world size {w}")
-    per = n // w
-    if n % w != 0 and not _WARNED_RAGGED:
-        _WARNED_RAGGED = True
-        if r == 0:
-            print(f"timegan_b200.dist: global batch {n} not divisible by {w} ranks; using the first {per * w} sequences")
-    return x[r * per:(r + 1) * per]
+        _SHARD = None
+        return None
+    a, b = shard_bounds(n, w, r)
+    _SHARD = (b - a, n)
+    return x[a:b]
+
+
+def clear_shard():
+    """Forget the shard bookkeeping (callers that hand every rank its own equal-sized batch, e.g. bench.py)."""
+    global _SHARD
+    _SHARD = None

@@ -65,6 +65,7 @@ def main(argv=None):
         run_dir = out_root / fp.stem
         print(f"\n=== Training {fp.name} → {run_dir} ===")
         tt.train_single_npz(npz_path=fp, out_dir=run_dir, device=device, **kw)
+    _dist.shutdown()
     print("\nAll models trained. Checkpoints, logs, and synthetic data are under:", out_root)
 
 

@@ -249,9 +249,13 @@ class AsyncCheckpointer:
         return obj
 
     def save(self, path: Path, model: TimeGAN, optG, optD, step: int, meta: Dict):
+        self.save_state(path, {"step": step, "model": model.state_dict(), "optG": optG.state_dict(),
+                               "optD": optD.state_dict(), "meta": dict(meta)})
+
+    def save_state(self, path: Path, state: Dict):
+        """Write an already assembled checkpoint dict (same schema) behind the training stream."""
         self.wait()
-        state = self._snapshot({"step": step, "model": model.state_dict(), "optG": optG.state_dict(),
-                                "optD": optD.state_dict(), "meta": dict(meta)})
+        state = self._snapshot(state)
         ev = None
         if torch.cuda.is_available():
             ev = torch.cuda.Event()
@@ -278,6 +282,76 @@ class AsyncCheckpointer:
         if self._error is not None:
             e, self._error = self._error, None
             raise e
+
+
+class BestSnapshot:
+    """The reference's best-checkpoint rule (tt:410-413: `if g_total < best_ckpt_loss: save_ckpt(best_path, ...)`,
+    evaluated after EVERY step) without a host round trip per step.
+
+    A second copy of everything a checkpoint holds -- weights, spectral-norm buffers, both optimisers' Adam moments
+    -- lives in HBM.  update(g_total, step) is two launches (csrc/optim.cu `snapshot_if_better`): when the step's
+    generator loss beats the best so far, the live tensors are copied into the snapshot and (best, best_step) are
+    updated, all on the device.  The host reads `best_step` together with the logged scalars whenever it flushes
+    them, and only then -- if it moved -- hands the snapshot to the AsyncCheckpointer.  The file therefore holds
+    exactly the weights the reference would have saved, written at most once per flush window."""
+
+    def __init__(self, model: TimeGAN, optG, optD, device, best: float = math.inf):
+        import ctypes as C
+        self._C = C
+        for opt in (optG, optD):
+            for g in opt.param_groups:
+                for p in g["params"]:
+                    opt._init_state(p)
+        self.model, self.optG, self.optD = model, optG, optD
+        self.src = [t for t in model.state_dict().values() if t.is_cuda and t.dtype == torch.float32]
+        self.model_keys = [k for k, t in model.state_dict().items() if t.is_cuda and t.dtype == torch.float32]
+        self.n_model = len(self.src)
+        self.moment_owner = []
+        for name, opt in (("optG", optG), ("optD", optD)):
+            for g in opt.param_groups:
+                for p in g["params"]:
+                    for k in ("exp_avg", "exp_avg_sq"):
+                        self.src.append(opt.state[p][k])
+                        self.moment_owner.append((name, p, k))
+        self.dst = [torch.empty_like(t) for t in self.src]
+        n = len(self.src)
+        self._dst_ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in self.dst])
+        self._src_ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in self.src])
+        self._sizes = (C.c_longlong * n)(*[t.numel() for t in self.src])
+        self.best = torch.full((1,), float(best), dtype=torch.float32, device=device)
+        self.best_step = torch.full((1,), -1.0, dtype=torch.float32, device=device)
+        self.written_step = -1
+
+    def update(self, g_total: torch.Tensor, step: int):
+        from ._lib import lib, check, ptr, stream_ptr
+        val = g_total.detach().reshape(1).float().contiguous()
+        check(lib.tg_snapshot_if_better(stream_ptr(), len(self.src), self._dst_ptrs, self._src_ptrs, self._sizes,
+                                        ptr(val), ptr(self.best), ptr(self.best_step), float(step)),
+              "tg_snapshot_if_better")
+
+    def checkpoint(self, best_step: int, now_step: int, meta: Dict, lr_at) -> Dict:
+        """The checkpoint dict of the snapshot (schema of tt:58-61).  `now_step` is the step the live optimisers are
+        at; their per-parameter `step` counters are rewound by (now_step - best_step); `lr_at(name, step)` gives the
+        scheduled learning rate of optimiser `name` after `step` GAN steps."""
+        snap = dict(zip(self.model_keys, self.dst[:self.n_model]))
+        model_sd = type(self.model.state_dict())((k, snap.get(k, v)) for k, v in self.model.state_dict().items())
+        moments = {(name, id(p), k): t for (name, p, k), t in zip(self.moment_owner, self.dst[self.n_model:])}
+        out = {"step": best_step, "model": model_sd, "meta": dict(meta, best=True)}
+        for name, opt in (("optG", self.optG), ("optD", self.optD)):
+            sd = opt.state_dict()
+            idx = 0
+            for g, g_live in zip(sd["param_groups"], opt.param_groups):
+                g["lr"] = lr_at(name, best_step)
+                for p in g_live["params"]:
+                    st = dict(sd["state"].get(idx, {}))
+                    if st:
+                        st["exp_avg"] = moments[(name, id(p), "exp_avg")]
+                        st["exp_avg_sq"] = moments[(name, id(p), "exp_avg_sq")]
+                        st["step"] = torch.tensor(float(st["step"]) - float(now_step - best_step), dtype=torch.float32)
+                        sd["state"][idx] = st
+                    idx += 1
+            out[name] = sd
+        return out
 
 
 def sample_noise(batch_size: int, seq_len: int, z_dim: int, device, noise=None):
@@ -386,6 +460,8 @@ def phase_autoencoder(model: TimeGAN, loader: DataLoader, device, optER: optim.O
         n = 0
         for (x_batch,) in loader:
             x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+            if x is None:              # fewer sequences than ranks: skipped on every rank alike
+                continue
             _dist.begin_step("AE")
             x_tilde = model.reconstruct(x)
             loss = recon_loss(x, x_tilde)
@@ -409,6 +485,8 @@ def phase_supervisor(model: TimeGAN, loader: DataLoader, device, optS: optim.Opt
         n = 0
         for (x_batch,) in loader:
             x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+            if x is None:
+                continue
             _dist.begin_step("SUP")
             with torch.no_grad():
                 h = model.encode(x)
@@ -461,7 +539,7 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
     d_fake = D.head(yl_f)                                                            # power iteration 2 (tt:193)
 
     loss_bce = 0.5 * (bce(d_real, y_real) + bce(d_fake, y_fake))                    # tt:196
-    Bg = B * _dist.world_size()
+    Bg = _dist.global_count(B)
 
     r1 = None
     obj = loss_bce
@@ -674,18 +752,22 @@ def train_single_npz(npz_path: Path, out_dir: Path,
                      hidden_dim: Optional[int] = None,
                      noise: Optional[str] = None,
                      proj_dtype: str = "fp32",
-                     log_every: int = 1,
-                     graph: bool = False,
+                     log_every: Optional[int] = None,
+                     graph: Optional[bool] = None,
                      resident_data: bool = True,
                      resume: bool = False,
                      ckpt_every: int = 500,
                      stop_after: Optional[int] = None):
     """Same schedule, logs and artefacts as the reference.  Extras (keyword-only): `z_dim`/`hidden_dim`
     override adaptive_dims; `noise="host"` replays the reference's CPU random stream (parity runs), default is
-    on-device Philox; `proj_dtype` "fp32" | "bf16" (tensor-core input projections); `log_every` k > 1 keeps
-    the per-step scalars on the device and flushes CSV rows / best-checkpoint decisions every k steps;
-    `graph=True` replays the joint step from a CUDA graph (GraphedJointStep; full-size batches only -- the ragged
-    last batch of an epoch runs eagerly -- on-device noise); `resident_data` keeps the dataset in HBM and gathers
+    on-device Philox; `proj_dtype` "fp32" | "bf16" (tensor-core input projections).
+    The default path is the fast path: every step still gets its CSV row and the reference's per-step
+    best-checkpoint rule is still applied to every step (on the device, `BestSnapshot`), but the host only
+    synchronises with the GPU every `log_every` steps (default 25; 1 with host-replayed noise) to write the rows
+    and hand a changed best snapshot to the asynchronous writer; `graph` (default: on whenever the noise is
+    on-device and, under data parallelism, the all-reduces are the peer-memory kernels) replays the joint step
+    from a CUDA graph (GraphedJointStep; full-size batches only -- the ragged last batch of an epoch runs
+    eagerly); `resident_data` keeps the dataset in HBM and gathers
     batches on the device in the reference's shuffle order (DeviceLoader); `resume=True` continues the GAN phase
     from `out_dir/ckpt_latest.pt` (weights, both optimisers, LR schedules, noise decay, step counter) instead of
     starting over -- the reference can only start over; `ckpt_every` is the reference's hard-coded 500 (tt:406);
@@ -740,9 +822,12 @@ def train_single_npz(npz_path: Path, out_dir: Path,
         optS = FusedAdam(model.supervisor.parameters(), lr=lr_g, betas=betas)
         phase_supervisor(model, loader, device, optS, grad_clip, sup_epochs, LOG)
 
-    # under data parallelism the step can only be captured when the all-reduces are this package's own peer-memory
-    # kernels (dist.PeerComm); NCCL collectives are issued eagerly
-    use_graph = bool(graph) and nz is None and (not _dist.is_enabled() or _dist.peer_comm() is not None)
+    # CUDA-graph replay is the default whenever it is possible: on-device noise, and under data parallelism the
+    # all-reduces must be this package's own peer-memory kernels (dist.PeerComm); NCCL collectives are issued eagerly
+    can_graph = nz is None and (not _dist.is_enabled() or _dist.peer_comm() is not None)
+    use_graph = can_graph if graph is None else (bool(graph) and can_graph)
+    if log_every is None:
+        log_every = 1 if nz is not None else 25
     optD = FusedAdam(model.discriminator.parameters(), lr=lr_d, betas=betas, capturable=use_graph)
     optG = FusedAdam(_params(model.generator, model.supervisor, model.embedder, model.recovery), lr=lr_g, betas=betas,
                      capturable=use_graph)
@@ -767,19 +852,27 @@ def train_single_npz(npz_path: Path, out_dir: Path,
                 schedulerG.step()
                 schedulerD.step()
 
+    def lr_at(name, st):
+        base = lr_g if name == "optG" else lr_d
+        return base * (0.5 ** sum(1 for m in milestones if st >= m))
+
+    # on-device noise: one Philox stream per call, keyed by (seed, rank, step the run starts at) -- a second call in
+    # the same process (main()'s loop over files, another seed) starts its own stream instead of continuing the first
     step_noise = nz
-    if start_step and nz is None:
-        # a fresh Philox stream for the continued run (the default stream would restart at its first draw)
-        step_noise = device_noise(torch.initial_seed() + 7919 * _dist.rank() + 104729 * start_step, device)
+    if nz is None:
+        step_noise = device_noise(int(seed) * 1000003 + 7919 * _dist.rank() + 104729 * start_step, device)
     loader_iter = iter(loader)
     noise_decay = (inst_noise_start - inst_noise_end) / max(1, gan_steps)
     inst_noise = max(inst_noise_end, inst_noise_start - noise_decay * start_step)
     best_ckpt_loss = math.inf
-    saver = AsyncCheckpointer()
+    if resume_state is not None:        # the best loss seen before the interruption (kept in the checkpoint's meta)
+        best_ckpt_loss = float(resume_state.get("meta", {}).get("best_loss", math.inf))
+    saver, best_saver = AsyncCheckpointer(), AsyncCheckpointer()
     meta = {"npz": npz_path.name, "z_dim": z_dim, "h_dim": h_dim}
     target = 0.5 * (d_min_acc + d_max_acc)
     band = max(0.0, d_max_acc - d_min_acc)
     pending = []   # (step, device scalars) awaiting a flush
+    snap = BestSnapshot(model, optG, optD, device, best_ckpt_loss) if rank0 else None
     graphed = None
     if use_graph:
         graphed = GraphedJointStep(model, optD, optG, device, label_smooth=label_smooth, clip=grad_clip,
@@ -787,11 +880,17 @@ def train_single_npz(npz_path: Path, out_dir: Path,
                                    beta_rec=beta_rec, gamma_cov=gamma_cov, gamma_acf=gamma_acf, acf_max_lag=acf_max_lag,
                                    schedulerD=schedulerD, schedulerG=schedulerG, noise=step_noise)
 
-    def flush():
+    def flush(now_step):
+        """ONE device->host transfer for every step logged since the last flush: CSV rows, the [GAN] progress lines,
+        the best-checkpoint bookkeeping and the health checks of the data-parallel transport."""
         nonlocal best_ckpt_loss
         if not pending:
             return
-        vals = torch.stack([torch.stack([v.float().reshape(()) for v in row]) for _, row in pending]).cpu().tolist()
+        rows_dev = [torch.stack([v.float().reshape(()) for v in row]) for _, row in pending]
+        tail = [snap.best.reshape(()), snap.best_step.reshape(())] if snap is not None else []
+        flat = torch.cat([torch.stack(rows_dev).reshape(-1)] + [torch.stack(tail)] if tail else
+                         [torch.stack(rows_dev).reshape(-1)]).cpu().tolist()
+        vals = [flat[i * 8:(i + 1) * 8] for i in range(len(pending))]
         rows = []
         for (st, _), r in zip(pending, vals):
             rows.append([st, "GAN"] + r)
@@ -801,12 +900,15 @@ def train_single_npz(npz_path: Path, out_dir: Path,
         if rank0:
             with open(log_file, "a", newline="") as f:
                 csv.writer(f).writerows(rows)
-        last_step, last = rows[-1][0], rows[-1]
-        # best checkpoint (tt:410-413): with log_every == 1 this is the reference's per-step rule; with k > 1
-        # the current weights are saved when the LAST step of the window improved on the best seen so far.
-        if last[4] < best_ckpt_loss and rank0:
-            save_ckpt(best_path, model, optG, optD, last_step, dict(meta, best=True))
-        best_ckpt_loss = min([best_ckpt_loss] + [r[4] for r in rows])
+        if _dist.peer_comm() is not None:
+            _dist.peer_comm().check_status()        # a rank that timed out waiting for a peer poisons its sums: stop here
+        if snap is not None:
+            best_ckpt_loss, best_step = float(flat[-2]), int(flat[-1])
+            if best_step >= 0 and best_step != snap.written_step:
+                # tt:410-413: the weights after the step with the lowest g_total so far -- captured on the device at
+                # that step, written now (behind the training stream)
+                best_saver.save_state(best_path, snap.checkpoint(best_step, now_step, meta, lr_at))
+                snap.written_step = best_step
         pending.clear()
 
     for step in range(start_step + 1, gan_steps + 1):
@@ -816,30 +918,44 @@ def train_single_npz(npz_path: Path, out_dir: Path,
             loader_iter = iter(loader)
             (x_batch,) = next(loader_iter)
         x = _dist.shard_batch(x_batch.to(device, non_blocking=True))
+        if x is None:
+            # fewer sequences than ranks (tail of an epoch under data parallelism): every rank sees the same count and
+            # skips the batch; the step still counts so that schedules and checkpoints stay aligned with the reference
+            schedulerD.step(); schedulerG.step()
+            inst_noise = max(inst_noise_end, inst_noise - noise_decay)
+            continue
 
-        if graphed is not None and x.shape[0] == batch_size // _dist.world_size() and inst_noise > 0:
+        if graphed is not None and x.shape[0] * _dist.world_size() == batch_size and inst_noise > 0:
             vals = graphed(x, inst_noise).clone()           # the graph's output buffer is reused by the next replay
-            pending.append((step, tuple(vals.unbind(0))))
+            row = tuple(vals.unbind(0))
         else:
             d_loss, d_acc = disc_step(model, x, device, optD, label_smooth, inst_noise, grad_clip, schedulerD, r1_gamma,
                                       target_acc=target, band=band, noise=step_noise, sync=False)
             g_vals = gen_step(model, x, device, optG, alpha_sup, beta_rec, inst_noise, grad_clip, schedulerG, gamma_cov,
                               gamma_acf, acf_max_lag, noise=step_noise, sync=False)
-            pending.append((step, (d_loss, d_acc) + tuple(g_vals)))
-        if len(pending) >= max(1, log_every) or step == gan_steps:
-            flush()
+            row = (d_loss, d_acc) + tuple(g_vals)
+        pending.append((step, row))
+        if snap is not None:
+            snap.update(row[2], step)
+        stopping = stop_after is not None and step >= stop_after
+        ckpt_now = step % max(1, ckpt_every) == 0 or step == gan_steps or stopping
+        if len(pending) >= max(1, log_every) or ckpt_now:
+            flush(step)
 
         inst_noise = max(inst_noise_end, inst_noise - noise_decay)
-        stopping = stop_after is not None and step >= stop_after
-        if (step % max(1, ckpt_every) == 0 or step == gan_steps or stopping) and rank0:
-            flush()
-            saver.save(ckpt_path, model, optG, optD, step, meta)     # written behind the training stream
+        if ckpt_now and rank0:
+            saver.save(ckpt_path, model, optG, optD, step, dict(meta, best_loss=best_ckpt_loss))   # behind the stream
         if stopping:
-            flush()
             saver.wait()
+            best_saver.wait()
             LOG(f"[stop] stop_after={stop_after}: checkpoint at step {step}, resume with resume=True")
             return
     saver.wait()
+    best_saver.wait()
+    dump = os.environ.get("TIMEGAN_B200_DUMP_WEIGHT_SUM")
+    if dump:    # DP self-check hook: every rank records an exact fingerprint of its final weights (replicas must agree)
+        fp = [float(p.detach().double().sum().item()) for p in model.parameters()]
+        Path(dump, f"weight_sum_rank{_dist.rank()}.txt").write_text(repr(fp))
 
     model.eval()
     from .generate_long_synth import generate_windows
@@ -886,8 +1002,11 @@ def build_argparser():
     ap.add_argument("--hidden_dim", type=int, default=None, help="override adaptive_dims' hidden size")
     ap.add_argument("--proj_dtype", type=str, default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--noise", type=str, default=None, choices=[None, "host"])
-    ap.add_argument("--log_every", type=int, default=1)
-    ap.add_argument("--graph", action="store_true", help="replay the joint step from a CUDA graph")
+    ap.add_argument("--log_every", type=int, default=None,
+                    help="GAN steps between host synchronisations (CSV rows are per step either way); default 25")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=None,
+                    help="replay the joint step from a CUDA graph (default: on whenever possible)")
+    ap.add_argument("--no_graph", dest="graph", action="store_false", help="issue every step eagerly")
     ap.add_argument("--resume", action="store_true", help="continue the GAN phase from <out_dir>/ckpt_latest.pt")
     ap.add_argument("--ckpt_every", type=int, default=500, help="GAN steps between ckpt_latest.pt writes")
     return ap
@@ -895,7 +1014,7 @@ def build_argparser():
 
 def main(argv=None):
     args = build_argparser().parse_args(argv)
-    _dist.init()
+    _dist.init()                      # under torchrun: cuda:LOCAL_RANK becomes the current device, peer transport on
     device = device_autoselect()
     print(f"Using device: {device}")
     out_root = Path(args.out_dir)
@@ -915,6 +1034,7 @@ def main(argv=None):
             acf_max_lag=args.acf_max_lag, device=device, z_dim=args.z_dim, hidden_dim=args.hidden_dim,
             proj_dtype=args.proj_dtype, noise=args.noise, log_every=args.log_every, graph=args.graph,
             resume=args.resume, ckpt_every=args.ckpt_every)
+    _dist.shutdown()
 
 
 if __name__ == "__main__":

@@ -153,6 +153,13 @@ int tg_adam(void* stream, int n, float* const* params, const float* const* grads
             float* dev_state /* NULL, or device float[4] {lr, step, -, -}: the step counter and bias corrections
                                 then live on the device (CUDA-graph replay); `lr`/`step` arguments are ignored */);
 
+/* Best-checkpoint rule of train_timegan.py:410-413 ("if g_total < best_ckpt_loss: save_ckpt(best_path, ...)") without
+ * a host round trip per step: when value[0] < best[0] (both device floats) the n source tensors (weights, Adam
+ * moments) are copied into the snapshot tensors `dst`, then best[0] = value[0] and best_step[0] = step.  The host
+ * reads best_step at its own pace and writes the snapshot to ckpt_best.pt when it has changed. */
+int tg_snapshot_if_better(void* stream, int n, float* const* dst, const float* const* src, const long long* sizes,
+                          const float* value, float* best, float* best_step, float step);
+
 /* ---- noise (train_timegan.py:64-65 sample_noise, :46-47 add_instance_noise, :40-43 smooth_labels) --------
  * Philox4x32-10 keyed by (seed, offset); each call consumes ceil(n/4) counter values. */
 int tg_rng_uniform(void* stream, float* out, long long n, unsigned long long seed, unsigned long long offset, float lo,

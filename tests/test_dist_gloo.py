@@ -30,9 +30,25 @@ def _worker(rank, world, port, ret):
         w = torch.rand(3, generator=g).requires_grad_(True)  # a "parameter"
         xs = D.shard_batch(X)
         assert xs.shape[0] == 8 // world and torch.equal(xs, X[rank * 4:(rank + 1) * 4])
-        assert D.shard_batch(X[:7]).shape[0] == 3          # ragged tail trimmed to a multiple of the world size
-        with pytest.raises(ValueError):
-            D.shard_batch(X[:1])
+        # --- ragged global batch (drop_last=False, tt:33-37): every sequence is used, shards differ by one, and the
+        #     statistics stay exact because they are count-weighted sums over the GLOBAL count ---
+        xr = D.shard_batch(X[:7])
+        assert xr.shape[0] == (4 if rank == 0 else 3) and torch.equal(xr, X[:7][0:4] if rank == 0 else X[:7][4:7])
+        assert D.global_count(xr.shape[0]) == 7.0 and D.global_count(xr.numel()) == float(X[:7].numel())
+        s7, n7 = D.allreduce_stats(xr.sum((0, 1)), xr.shape[0] * xr.shape[1])
+        assert n7 == 35.0 and torch.allclose(s7, X[:7].sum((0, 1)), atol=1e-6)
+        wr = torch.rand(3, generator=torch.Generator().manual_seed(5)).requires_grad_(True)
+        lm = D.global_mean(((xr * wr).sum(-1) ** 2).sum(), xr.shape[0] * xr.shape[1])
+        lm.backward()
+        wref = wr.detach().clone().requires_grad_(True)
+        ref7 = (((X[:7] * wref).sum(-1)) ** 2).mean()
+        ref7.backward()
+        assert torch.allclose(lm.detach(), ref7.detach(), atol=1e-6)
+        gb = D.GradBuckets(); gb.launch([wr]); gb.wait()     # SUM of the local contributions = the global gradient
+        assert torch.allclose(wr.grad, wref.grad, atol=1e-6), (wr.grad, wref.grad)
+        assert D.shard_batch(X[:1]) is None                  # fewer sequences than ranks: skipped on every rank alike
+        assert D.shard_bounds(9, 8, 0) == (0, 2) and D.shard_bounds(9, 8, 7) == (8, 9)
+        xs = D.shard_batch(X)                                # back to the even split for the checks below
         # --- statistics all-reduce: sum + global count ---
         s, n = D.allreduce_stats(xs.sum((0, 1)), xs.shape[0] * xs.shape[1])
         assert n == 40 and torch.allclose(s, X.sum((0, 1)), atol=1e-6)

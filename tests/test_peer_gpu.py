@@ -57,3 +57,29 @@ def test_dp_equals_single_process_and_graph_equals_eager_two_ranks():
     assert r.returncode == 0 and r.stdout.count("-> OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
     r = _torchrun2("check_dp_graph.py", 29535)
     assert r.returncode == 0 and r.stdout.count("-> OK") == 2, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box")
+def test_cli_under_torchrun_two_ranks(tmp_path):
+    """`torchrun --nproc-per-node 2 -m timegan_b200.train_timegan ...`: each rank takes
+    cuda:LOCAL_RANK, the peer transport comes up (so the default CUDA-graph path is used), a ragged epoch tail
+    (13 windows, batch 4 -> 4,4,4,1: the last batch has fewer sequences than ranks and is skipped on both) trains
+    through, rank 0 writes the artefacts, and both ranks end with bit-identical weights."""
+    import numpy as np
+    data = tmp_path / "preprocessed"
+    data.mkdir()
+    np.savez(data / "posture1_no_exo.npz", X=np.random.default_rng(3).random((13, 32, 14), dtype=np.float32))
+    env = dict(os.environ, PYTHONPATH=str(ROOT), TIMEGAN_B200_DUMP_WEIGHT_SUM=str(tmp_path))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29536", "-m", "timegan_b200.train_timegan",
+                        "--data_dir", str(data), "--out_dir", str(tmp_path / "runs"), "--batch_size", "4",
+                        "--ae_epochs", "1", "--sup_epochs", "1", "--gan_steps", "9", "--layers", "2", "--z_dim", "8",
+                        "--hidden_dim", "8", "--acf_max_lag", "8"],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "Using device: cuda:0" in r.stdout and "Using device: cuda:1" in r.stdout
+    run = tmp_path / "runs" / "posture1_no_exo"
+    assert (run / "ckpt_latest.pt").exists() and (run / "synthetic.npz").exists()
+    sums = [(tmp_path / f"weight_sum_rank{k}.txt").read_text() for k in (0, 1)]
+    assert sums[0] == sums[1], sums

@@ -191,5 +191,7 @@ def test_generate_long_synth_cli_on_the_shipped_run(tmp_path):
     b = np.load(runs / "posture1_no_exo" / "synthetic_T1000.npz")["X"]
     assert b.shape == (5, 1000, 14) and np.isfinite(b).all()
     sc = np.load(real / "posture1_no_exo.npz")
-    lo, hi = sc["scale_min"], sc["scale_min"] + sc["scale_range"]
-    assert (b.mean((0, 1)) > lo - 0.5 * sc["scale_range"]).all() and (b.mean((0, 1)) < hi + 0.5 * sc["scale_range"]).all()
+    # --denorm maps the scaled space back to microvolts with the NPZ's per-channel affine map (gl:123-126): the spread
+    # of every channel is a sizeable fraction of its recorded range, which no [0,1]-scaled output would have
+    sd = b.std((0, 1))
+    assert (sd > 0.02 * sc["scale_range"]).all() and (sd < 2.0 * sc["scale_range"]).all(), sd

@@ -35,7 +35,9 @@ def test_train_single_npz_eager_equals_graph_and_writes_reference_artefacts(tmp_
         logs[mode] = np.array([[float(r[c]) for c in list(r.keys())[2:]] for r in rows])
         assert np.isfinite(logs[mode]).all()
         ck = torch.load(out / "ckpt_latest.pt", map_location="cpu")
-        assert ck["step"] == 14 and ck["meta"] == {"npz": npz.name, "z_dim": 16, "h_dim": 16}
+        assert ck["step"] == 14
+        assert {k: ck["meta"][k] for k in ("npz", "z_dim", "h_dim")} == {"npz": npz.name, "z_dim": 16, "h_dim": 16}
+        assert ck["meta"]["best_loss"] == pytest.approx(min(float(r["loss_G"]) for r in rows), rel=1e-6)
         assert set(ck["optG"]["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
         assert float(ck["optG"]["state"][0]["step"]) == 14
         assert (out / "ckpt_best.pt").exists()
@@ -44,6 +46,83 @@ def test_train_single_npz_eager_equals_graph_and_writes_reference_artefacts(tmp_
     np.testing.assert_allclose(logs["graph"], logs["eager"], rtol=5e-3, atol=2e-5)
     text = capsys.readouterr().out
     assert "[AE] epoch 1/1" in text and "[SUP] epoch 1/1" in text and "Saved synthetic" in text
+
+
+def test_snapshot_if_better_kernel():
+    """csrc/optim.cu `snapshot_if_better`: the multi-tensor copy happens only when value < best, and (best, step)
+    follow (tt:410-413 evaluated on the device)."""
+    import ctypes as C
+    from timegan_b200._lib import lib, check, ptr, stream_ptr
+    dev = torch.device("cuda:0")
+    src = [torch.randn(n, device=dev) for n in (5, 4096, 10001)] * 20          # 60 tensors: two launches of <= 48
+    dst = [torch.zeros_like(t) for t in src]
+    n = len(src)
+    dp = (C.c_void_p * n)(*[t.data_ptr() for t in dst])
+    sp = (C.c_void_p * n)(*[t.data_ptr() for t in src])
+    sz = (C.c_longlong * n)(*[t.numel() for t in src])
+    best = torch.full((1,), float("inf"), device=dev)
+    bstep = torch.full((1,), -1.0, device=dev)
+
+    def call(v, step):
+        val = torch.tensor([v], device=dev)
+        check(lib.tg_snapshot_if_better(stream_ptr(), n, dp, sp, sz, ptr(val), ptr(best), ptr(bstep), float(step)), "snap")
+    call(2.0, 1)
+    assert best.item() == 2.0 and bstep.item() == 1.0 and all(torch.equal(a, b) for a, b in zip(dst, src))
+    old = [t.clone() for t in src]
+    for t in src:
+        t.add_(1.0)
+    call(3.0, 2)                                             # worse: nothing moves
+    assert best.item() == 2.0 and bstep.item() == 1.0 and all(torch.equal(a, b) for a, b in zip(dst, old))
+    call(2.0, 3)                                             # equal is not better (strict <, like the reference)
+    assert bstep.item() == 1.0
+    call(float("nan"), 4)                                    # NaN never wins
+    assert bstep.item() == 1.0
+    call(1.5, 5)
+    assert best.item() == 1.5 and bstep.item() == 5.0 and all(torch.equal(a, b) for a, b in zip(dst, src))
+
+
+def test_default_path_is_the_fast_path_and_keeps_the_per_step_best_rule(tmp_path):
+    """train_single_npz with DEFAULT extras: the joint step replays from the CUDA graph (inter-layer dropout 0.2
+    inside the captured step), the host synchronises every 25 steps only, every step still has its CSV row, and
+    ckpt_best.pt holds the weights AFTER THE STEP WITH THE LOWEST loss_G -- the reference's per-step rule (tt:410-413)
+    -- which a second run stopped at exactly that step reproduces."""
+    from timegan_b200 import train_timegan as tt
+    X = np.random.default_rng(5).random((32, 48, 14), dtype=np.float32)
+    npz = tmp_path / "posture2_no_exo.npz"
+    np.savez(npz, X=X, fs=128.0)
+    kw = dict(batch_size=8, ae_epochs=1, sup_epochs=1, gan_steps=40, layers=2, dropout=0.2, seed=11,
+              device=torch.device("cuda:0"), z_dim=16, hidden_dim=16, acf_max_lag=16)
+    seen = []
+    orig = tt.GraphedJointStep.__call__
+
+    def spy(self, x, std):
+        out = orig(self, x, std)
+        seen.append(self.graph is not None)
+        return out
+    tt.GraphedJointStep.__call__ = spy
+    try:
+        assert tt.train_single_npz(npz, tmp_path / "a", **kw) is True
+    finally:
+        tt.GraphedJointStep.__call__ = orig
+    assert len(seen) == 40 and sum(seen) >= 36                 # graph replay is what runs by default
+    rows = _rows(tmp_path / "a" / "train_log.csv")
+    assert [int(r["step"]) for r in rows] == list(range(1, 41))
+    g = np.array([float(r["loss_G"]) for r in rows])
+    assert np.isfinite(g).all()
+    best_step = int(np.argmin(g)) + 1                            # first step that reaches the minimum
+    ck = torch.load(tmp_path / "a" / "ckpt_best.pt", map_location="cpu", weights_only=False)
+    assert ck["step"] == best_step and ck["meta"]["best"] is True
+    assert float(ck["optG"]["state"][0]["step"]) == best_step and float(ck["optD"]["state"][0]["step"]) == best_step
+    lr = 1e-3 * 0.5 ** sum(best_step >= m for m in (20, 30))
+    assert ck["optG"]["param_groups"][0]["lr"] == pytest.approx(lr)
+    # same seed, stopped right after that step: its ckpt_latest is what the reference would have saved as best
+    tt.train_single_npz(npz, tmp_path / "b", stop_after=best_step, **kw)
+    ref = torch.load(tmp_path / "b" / "ckpt_latest.pt", map_location="cpu", weights_only=False)
+    assert ref["step"] == best_step
+    for k, v in ref["model"].items():
+        assert torch.allclose(ck["model"][k], v, rtol=1e-4, atol=1e-6), k
+    for i, st in ref["optG"]["state"].items():
+        assert torch.allclose(ck["optG"]["state"][i]["exp_avg"], st["exp_avg"], rtol=1e-3, atol=1e-7), i
 
 
 def test_main_config_route(tmp_path, monkeypatch):

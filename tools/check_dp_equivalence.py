@@ -1,7 +1,9 @@
 #!/usr/bin/env python3
 """torchrun --nproc-per-node 2 tools/check_dp_equivalence.py
-Two data-parallel ranks (NCCL), each holding half of a global batch, must reproduce the single-process joint steps
-on the whole batch: same losses (the batch statistics are all-reduced) and same updated weights."""
+Two data-parallel ranks, each holding its shard of a global batch, must reproduce the single-process joint steps
+on the whole batch: same losses (the batch statistics are all-reduced) and same updated weights --
+including a RAGGED global batch (7 sequences -> shards of 4 and 3: the count-weighted statistics of dist.py, the
+reference's drop_last=False tail of tt:33-37)."""
 import copy, os, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -13,20 +15,21 @@ class ShardedReplayNoise:
     """Draws the GLOBAL-batch tensor from the seeded CPU generator (reference order) and keeps this rank's slice."""
     def __init__(self, device, world, rank):
         self.device, self.world, self.rank = device, world, rank
+        self.n_global = None          # set before every step: sequences in the global batch
     def begin(self): pass
     def end(self): pass
-    def _slice(self, t, b):
-        return t[self.rank * b:(self.rank + 1) * b].contiguous().to(self.device)
+    def _slice(self, t):
+        from timegan_b200 import dist as D
+        a, b = D.shard_bounds(self.n_global, self.world, self.rank)
+        return t[a:b].contiguous().to(self.device)
     def rand(self, *shape):
-        b = shape[0]
-        return self._slice(torch.rand(b * self.world, *shape[1:]), b)
+        return self._slice(torch.rand(self.n_global, *shape[1:]))
     def randn_like(self, h, time_major=False):
-        b = h.shape[0]
         if time_major and h.dim() == 3:
-            like = torch.empty(h.shape[1], b * self.world, h.shape[2]).transpose(0, 1)
+            like = torch.empty(h.shape[1], self.n_global, h.shape[2]).transpose(0, 1)
         else:
-            like = torch.empty(b * self.world, *h.shape[1:])
-        return self._slice(torch.randn_like(like), b)
+            like = torch.empty(self.n_global, *h.shape[1:])
+        return self._slice(torch.randn_like(like))
 
 
 def main():
@@ -40,7 +43,7 @@ def main():
     torch.manual_seed(0)
     base = tg.TimeGAN(14, 24, 24, 2, 0.0)
     Bg, T = 8, 96
-    xs = [torch.rand(Bg, T, 14) for _ in range(3)]
+    xs = [torch.rand(Bg, T, 14), torch.rand(7, T, 14), torch.rand(Bg, T, 14)]      # the middle batch is ragged
     hp = dict(label_smooth=0.2, std=0.3, clip=0.5, r1=1.0, target=0.525, band=0.15, a=5.0, b=0.2, gc=0.05, ga=0.05, lag=32)
 
     def run(model, noise, shard):
@@ -50,6 +53,8 @@ def main():
         out = []
         for i, xg in enumerate(xs):
             torch.manual_seed(100 + i)
+            if hasattr(noise, "n_global"):
+                noise.n_global = xg.shape[0]
             x = (D.shard_batch(xg) if shard else xg).to(dev)
             d = tt.disc_step(model, x, dev, oD, hp["label_smooth"], hp["std"], hp["clip"], None, hp["r1"],
                              target_acc=hp["target"], band=hp["band"], noise=noise)
