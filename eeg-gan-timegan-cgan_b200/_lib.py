@@ -64,6 +64,10 @@ SIGNATURES = {
     "tg_sumsq": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_ll), _vp, _vp, _sz]),
     "tg_adam": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _vp,
                      _f, _f, _f, _f, _f, _i, _f, _vp]),
+    "tg_head_fwd": (_i, [_vp, _vp, _ll, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tg_head_seed": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, _f]),
+    "tg_head_bwd": (_i, [_vp, _vp, _ll, _vp, _ll] + [_vp] * 13 + [_i, _i, _f, _f]),
+    "tg_head_adv_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f]),
     "tg_snapshot_if_better": (_i, [_vp, _i, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_ll), _vp, _vp, _vp, _f]),
     "tg_rng_uniform": (_i, [_vp, _vp, _ll, _ull, _ull, _f, _f, _vp]),
     "tg_rng_add_normal": (_i, [_vp, _vp, _vp, _ll, _f, _ull, _ull, _vp]),

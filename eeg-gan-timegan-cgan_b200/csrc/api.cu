@@ -123,6 +123,33 @@ int tg_long_chunks() {
   return x;
 }
 
+// cluster kernels (gru_cluster.cu) for H = 128 / 256: 1 = where they are the faster kernel (default), 0 = never,
+// 2 = for every H = 128 / 256 launch (TIMEGAN_B200_CLUSTER / tg_set_option("cluster", v))
+static std::atomic<int> g_use_cluster{-1};
+int tg_use_cluster() {
+  int x = g_use_cluster.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_CLUSTER");
+    x = e ? atoi(e) : 1;
+    if (x < 0 || x > 2) x = 1;
+    g_use_cluster.store(x);
+  }
+  return x;
+}
+
+// two-columns-per-thread BPTT kernel for one-sequence-per-CTA launches at H <= 64 (gru_bwd.cu); TIMEGAN_B200_BWD_PAIR=0
+// / tg_set_option("bwd_pair", 0) switches back to the one-column kernel
+static std::atomic<int> g_bwd_pair{-1};
+int tg_bwd_pair() {
+  int x = g_bwd_pair.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_BWD_PAIR");
+    x = (e && atoi(e) == 0) ? 0 : 1;
+    g_bwd_pair.store(x);
+  }
+  return x;
+}
+
 static std::atomic<int> g_wgrad_cta_cap{0};
 int tg_wgrad_cta_cap() { return g_wgrad_cta_cap.load(std::memory_order_relaxed); }
 
@@ -148,6 +175,8 @@ const char* tg_last_error(void) { return g_err; }
 int tg_device_sm_count(void) { return tg_num_sms(); }
 int tg_set_option(const char* key, int value) {
   if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
+  if (key && strcmp(key, "bwd_pair") == 0) { g_bwd_pair.store(value ? 1 : 0); return TG_OK; }
+  if (key && strcmp(key, "cluster") == 0) { g_use_cluster.store(value < 0 || value > 2 ? 1 : value); return TG_OK; }
   if (key && strcmp(key, "peer_timeout_ms") == 0) { g_peer_timeout_ms.store(value < 1 ? 1 : value); return TG_OK; }
   tg_set_error("set_option: unknown key '%s'", key ? key : "(null)");
   return TG_ERR_ARG;
@@ -340,6 +369,32 @@ int tg_adam(void* stream, int n, float* const* params, const float* const* grads
   ProfScope _ps(stream, K_OPTIM, 0.0, 0.0);
   return tg_adam_multi_impl((cudaStream_t)stream, n, params, grads, exp_avg, exp_avg_sq, sizes, sumsq, max_norm, lr,
                             beta1, beta2, eps, step, grad_scale, dev_state);
+}
+
+int tg_head_fwd(void* stream, const float* y_last, long long ld, int B, int H, int n_half, const float* w,
+                const float* bias, float* u, float* v, int training, const float* labels, float* wbar, float* uv,
+                float* sigma, float* p, float* stats) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
+  return tg_head_fwd_impl((cudaStream_t)stream, y_last, ld, B, H, n_half, w, bias, u, v, training, labels, wbar, uv,
+                          sigma, p, stats);
+}
+int tg_head_seed(void* stream, const float* p, const float* labels, const float* wbar, const float* stats, float* scal,
+                 float* seed, float* gyf, int B, int H, float Bg, float target, float band) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
+  return tg_head_seed_impl((cudaStream_t)stream, p, labels, wbar, stats, scal, seed, gyf, B, H, Bg, target, band);
+}
+int tg_head_bwd(void* stream, const float* y_last, long long ld, const float* hd, long long ld_hd, const float* p,
+                const float* labels, const float* w, const float* wbar, const float* uv, const float* sigma,
+                const float* scal, const float* r1, float* gyr, float* ghd, float* gw, float* gb, float* loss_val, int B,
+                int H, float Bg, float gamma) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
+  return tg_head_bwd_impl((cudaStream_t)stream, y_last, ld, hd, ld_hd, p, labels, w, wbar, uv, sigma, scal, r1, gyr, ghd,
+                          gw, gb, loss_val, B, H, Bg, gamma);
+}
+int tg_head_adv_bwd(void* stream, const float* p, const float* wbar, const float* gout, float* gy, int B, int H,
+                    float Bg) {
+  ProfScope _ps(stream, K_LOSS, 0.0, 0.0);
+  return tg_head_adv_bwd_impl((cudaStream_t)stream, p, wbar, gout, gy, B, H, Bg);
 }
 
 int tg_snapshot_if_better(void* stream, int n, float* const* dst, const float* const* src, const long long* sizes,

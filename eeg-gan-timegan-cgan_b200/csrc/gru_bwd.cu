@@ -240,6 +240,168 @@ __global__ void __launch_bounds__(HP* G, (EXACT || bwd_min_blocks<HP, G>() == 1)
   pipe.drain();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// One sequence per CTA, TWO output columns per thread (the c2 regime: B <= 2 x SMs, H <= 64).
+//
+// The backward mat-vec contracts over the 3H-long dGH vector, three times the forward's h: with one output column per
+// lane group every lane fetches 3*H/G values for 3*H/G FMAs x ... -- 24 LDS.128 per 48 FFMA2 at H = 64, and ncu showed
+// the shared-memory pipe (LSU 42 %, short-scoreboard the top stall) as what separates this kernel from the forward
+// (profiles/r01_ncu_gru_bwd_hotloop.txt).  Here a group of FOUR lanes owns a PAIR of adjacent columns (k, k+1): lane q
+// holds rows {(i*4+q)*4..+3} of all three gates for both columns (the same 96 weight registers), so every fetched
+// float4 of dGH feeds four FFMA2 instead of two -- 12 LDS.128 per step.  The four partial sums of the two columns are
+// combined by an exchange (xor 2) + a butterfly add (xor 1); lanes 2c and 2c+1 of a group then both hold column c's
+// total and repeat the same few gate-derivative operations (identical values, identical addresses) instead of idling.
+template <int HP, int TC, int NST, bool EXACT>
+__global__ void __launch_bounds__(2 * HP, EXACT ? 3 : 2) gru_bwd_pair_kernel(BwdParams p) {
+  constexpr int L = 4;                  // lanes per column pair
+  constexpr int J = HP / L;             // rows per lane and gate
+  constexpr int HR = HP + DG_PAD;
+  static_assert(J % 4 == 0, "slice must be float4 granular");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const int kp = tid / L, ql = tid % L;
+  const int k = 2 * kp + (ql >> 1);     // the column this lane finishes
+  const int H = EXACT ? HP : p.H;
+  const int T = p.T;
+  const int b0 = blockIdx.x;
+
+  float* dgs = reinterpret_cast<float*>(smem_raw);                     // [2][3][HR]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dgs + 2 * 3 * HR);
+  float* stages = reinterpret_cast<float*>(smem_raw + ((2 * 3 * HR * 4 + NST * 8 + 127) / 128) * 128);
+
+  ChunkPipe<4, 1, TC, NST> pipe;
+  pipe.g[0] = const_cast<float*>(p.rzn); pipe.gst[0] = p.dgi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | TG_STRM_STORE; pipe.shift[0] = 0;
+  pipe.g[1] = const_cast<float*>(p.q);   pipe.gst[1] = p.dq;  pipe.w[1] = H;     pipe.mode[1] = TG_STRM_LOAD | TG_STRM_STORE; pipe.shift[1] = 0;
+  pipe.g[2] = const_cast<float*>(p.dy);  pipe.gst[2] = nullptr; pipe.w[2] = H;   pipe.mode[2] = p.dy_last ? 0 : TG_STRM_LOAD;  pipe.shift[2] = 0;
+  pipe.g[3] = const_cast<float*>(p.y);   pipe.gst[3] = nullptr; pipe.w[3] = H;   pipe.mode[3] = TG_STRM_LOAD;                  pipe.shift[3] = -1;
+  pipe.layout();
+  pipe.stages = stages; pipe.full = bars;
+  pipe.T = T; pipe.nb = 1; pipe.b0 = b0; pipe.NC = (T + TC - 1) / TC;
+  pipe.reverse = true; pipe.bulk = p.bulk != 0;
+
+  // wt[o][g][m]: rows jj = (i*L+ql)*4 + {0,1 | 2,3} (m = 2i, 2i+1) of gate g, column 2*kp + o
+  float2 wt[2][3][J / 2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < J / 4; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int jj = (i * L + ql) * 4 + c, kk = 2 * kp + o;
+          const float v = (kk < H && jj < H) ? p.whh[(size_t)(g * H + jj) * H + kk] : 0.f;
+          if (c & 1) wt[o][g][2 * i + (c >> 1)].y = v; else wt[o][g][2 * i + (c >> 1)].x = v;
+        }
+  for (int i = tid; i < 2 * 3 * HR; i += 2 * HP) dgs[i] = 0.f;
+
+  const bool act = EXACT || k < H;
+  const bool use_dy = !p.dy_last;
+  float carry = (p.dy_last && act) ? p.dy[(size_t)b0 * H + k] : 0.f;
+  pipe.start();
+  __syncthreads();
+
+  const uint32_t dgs_addr = smem_u32(dgs);
+  const uint32_t h_step = 4u * (uint32_t)H, g_step = 12u * (uint32_t)H;
+  const uint32_t lane_k = 16u * (uint32_t)ql;
+  float fA, fB, fC, fr, fz, fdy;
+  uint32_t a_g, a_q, a_dy, a_h;
+
+  auto fetch = [&](bool first_t) __attribute__((always_inline)) {
+    const float r = lds_f32(a_g), z = lds_f32(a_g + h_step), n = lds_f32(a_g + 2u * h_step);
+    const float qv = lds_f32(a_q);
+    float hp = lds_f32(a_h);
+    hp = first_t ? 0.f : hp;
+    float dyv = lds_f32(a_dy);
+    dyv = use_dy ? dyv : 0.f;
+    const float omz = 1.f - z;
+    fA = omz * fmaf(-n, n, 1.f);
+    fB = (hp - n) * (z * omz);
+    fC = qv * (r * (1.f - r));
+    fr = r; fz = z; fdy = dyv;
+  };
+
+  int par = 0;
+  for (int c = 0; c < pipe.NC; ++c) {
+    pipe.acquire(c);
+    const int s = c % NST;
+    const int t0 = pipe.t0_of(c);
+    const int tcn = pipe.tcn_of(c);
+    const int kk = act ? k : 0;
+    a_g = pipe.row_addr(s, 0, 0, tcn - 1) + 4u * (uint32_t)kk;
+    a_q = pipe.row_addr(s, 1, 0, tcn - 1) + 4u * (uint32_t)kk;
+    a_dy = pipe.row_addr(s, 2, 0, tcn - 1) + 4u * (uint32_t)kk;
+    a_h = pipe.row_addr(s, 3, 0, tcn - 1) + 4u * (uint32_t)kk;
+    fetch(t0 + tcn - 1 == 0);
+    for (int tl = tcn - 1; tl >= 0; --tl) {
+      const bool last = (tl == 0);
+      // ---- gate derivatives of step t: three dependent FP32 ops after the carry arrives ----
+      const uint32_t dg = dgs_addr + (uint32_t)(par * 3 * HR) * 4u;
+      const float dh = fdy + carry;
+      const float dan = dh * fA;
+      const float daz = dh * fB;
+      const float dar = dan * fC;
+      const float dqv = dan * fr;
+      const float cz = dh * fz;
+      if (act) {
+        const uint32_t d = dg + (uint32_t)k * 4u;
+        sts_f32(d, dar); sts_f32(d + HR * 4u, daz); sts_f32(d + 2u * HR * 4u, dqv);
+        sts_f32(a_g, dar); sts_f32(a_g + h_step, daz); sts_f32(a_g + 2u * h_step, dan);
+        sts_f32(a_q, dqv);
+      }
+      a_g -= g_step; a_q -= h_step; a_dy -= h_step; a_h -= h_step;
+      if (last && pipe.bulk) fence_async_smem();
+      __syncthreads();
+      if (!last) fetch(t0 + tl - 1 == 0);      // step t-1's operands, fetched behind the mat-vec
+      // ---- W_hh^T dGH_t for the two columns of this lane group ----
+      float2 acc[2][3];
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) acc[o][g] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < J / 4; ++i)
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const float4 dv = lds_v4(dg + (uint32_t)(g * HR) * 4u + (uint32_t)(i * L) * 16u + lane_k);
+          const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            acc[o][g] = __ffma2_rn(wt[o][g][2 * i], d01, acc[o][g]);
+            acc[o][g] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[o][g]);
+          }
+        }
+      float u[2];
+#pragma unroll
+      for (int o = 0; o < 2; ++o)
+        u[o] = ((acc[o][0].x + acc[o][0].y) + (acc[o][1].x + acc[o][1].y)) + (acc[o][2].x + acc[o][2].y);
+      const bool hi = (ql & 2) != 0;
+      const float send = hi ? u[0] : u[1], keep = hi ? u[1] : u[0];
+      float v = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      carry = cz + v;
+      par ^= 1;
+    }
+    pipe.release(c);
+  }
+  pipe.drain();
+}
+
+template <int HP, int TC, int NST>
+int launch_bwd_pair(cudaStream_t st, const BwdParams& p) {
+  const int widths[4] = {3 * p.H, p.H, p.H, p.H};
+  constexpr int HR = HP + DG_PAD;
+  size_t smem = ((2 * 3 * HR * 4 + NST * 8 + 127) / 128) * 128 +
+                (size_t)NST * ChunkPipe<4, 1, TC, NST>::stage_floats_for(widths) * 4;
+  const bool exact = (p.H == HP);
+  auto kern = exact ? gru_bwd_pair_kernel<HP, TC, NST, true> : gru_bwd_pair_kernel<HP, TC, NST, false>;
+  if (exact) { TG_OPT_IN_SMEM((gru_bwd_pair_kernel<HP, TC, NST, true>), "gru_bwd_pair"); }
+  else { TG_OPT_IN_SMEM((gru_bwd_pair_kernel<HP, TC, NST, false>), "gru_bwd_pair"); }
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_bwd_pair: needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
+  kern<<<p.B, 2 * HP, smem, st>>>(p);
+  return tg_check_launch("gru_bwd_pair");
+}
+
 template <int HP, int G, int BT, int TC, int NST>
 int launch_bwd(cudaStream_t st, const BwdParams& p) {
   const int widths[4] = {3 * p.H, p.H, p.H, p.H};
@@ -261,6 +423,10 @@ int dispatch_bt(cudaStream_t st, const BwdParams& p, int bt) {
   constexpr int TC = 8, NST = 3;   // 8-step chunks (H = 128 used 4: twice the per-chunk ring cost per step)
   // one sequence per CTA (the co-resident, latency-bound regime): 16-step chunks halve the per-chunk cost of the
   // bulk-copy ring (thread 0 issues the stores/loads while the other warps wait at the next barrier)
+  if constexpr (HP <= 64) {
+    // one sequence per CTA: the two-columns-per-thread kernel (half the shared-memory operand traffic)
+    if (bt == 1 && tg_bwd_pair()) return tg_long_chunks() ? launch_bwd_pair<HP, 2 * TC, NST>(st, p) : launch_bwd_pair<HP, TC, NST>(st, p);
+  }
   if (HP <= 64 && bt == 1 && tg_long_chunks()) return launch_bwd<HP, G, 1, 2 * TC, NST>(st, p);
   switch (bt) {
     case 1: return launch_bwd<HP, G, 1, TC, NST>(st, p);
@@ -277,6 +443,10 @@ int tg_gru_bwd_impl(cudaStream_t st, const float* dy, const float* rzn, const fl
                     const float* whh, float* dgi, float* dq, int B, int T, int H, int flags, const float* whh_t) {
   TG_REQUIRE(dy && rzn && q && y && whh && dgi && dq, TG_ERR_ARG, "gru_bwd: null pointer");
   TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_bwd: bad shape B=%d T=%d H=%d", B, T, H);
+  const int dyl = (flags & TG_GRU_DY_LAST) ? 1 : 0;
+  if (tg_cluster_takes(H, B, true) && !(flags & TG_GRU_NO_BULK) && tg_aligned16(rzn) && tg_aligned16(q) && tg_aligned16(y) &&
+      tg_aligned16(dgi) && tg_aligned16(dq) && (dyl || tg_aligned16(dy)))
+    return tg_gru_cl_bwd(st, dy, rzn, q, y, whh, dgi, dq, B, T, H, dyl);
   if (H > 128) {
     TG_REQUIRE(whh_t, TG_ERR_ARG, "gru_bwd: hidden size %d > 128 needs the transposed weight (w_hh_t)", H);
     return tg_bigh_bwd(st, dy, rzn, q, y, whh_t, dgi, dq, B, T, H, (flags & TG_GRU_DY_LAST) ? 1 : 0);

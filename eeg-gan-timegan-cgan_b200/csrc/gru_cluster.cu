@@ -1,0 +1,594 @@
+// Resident GRU recurrences for hidden sizes whose W_hh does not fit ONE SM's register file: thread-block CLUSTERS.
+//
+//   H = 128 (BASELINE config c3):  W_hh = 196 KB  ->  cluster of 2 CTAs, each holds the 3 x 64 gate rows of 64 hidden units
+//   H = 256 (config c4's top end): W_hh = 786 KB  ->  cluster of 8 CTAs, 32 hidden units each
+// Every CTA has 256 threads with 96 weight registers each (98 KB of W_hh per SM, resident for all T steps), so the
+// kernels run one CTA per SM with a 255-register budget: no spills (the one-SM H = 128 kernels of gru_fwd.cu / gru_bwd.cu
+// are capped at 128 registers by their 512 threads and spill in the hot loop; H = 256 used to stream W_hh from L2 every
+// step, gru_bigh.cu).  Replaces the same reference code: the nn.GRU time loop of timegan_model.py:32-34 and autograd's
+// backward of it (train_timegan.py:140,159,219,267) -- SURVEY.md A.1 / A.2.
+//
+// Per timestep the CTAs of a cluster ALL-GATHER the new state through distributed shared memory: the lane that owns
+// (hidden unit j, sequence b) writes h_t[b][j] (BPTT: the three dGH values) into every CTA's double-buffered state
+// vector with `st.async ... mbarrier::complete_tx::bytes`, i.e. the remote store itself signals the receiving CTA's
+// mbarrier -- no cluster-wide barrier, no flag polling, no fence; a CTA waits on its OWN mbarrier (hardware-suspended
+// try_wait) until the H*G values of the step have landed.  The values of four consecutive hidden units are first
+// gathered into one lane by warp shuffles so that a store carries 16 bytes: 64 x CS stores per CTA and step.
+// (Measured at H = 128, B = 256, forward: one 4-byte st.async per value 2265 clk/step; plain st.shared::cluster stores +
+// one release-arrive per warp 3031 clk/step -- the cluster-scope release waits for the remote stores' acknowledgements.)
+// Two barriers (step parity) per sequence group suffice: a CTA can be at most one step ahead of its slowest peer,
+// because it needs that peer's values to finish a step.
+//
+// Forward lane mapping: G = 256/HU lanes per hidden unit, lane q holds the k-slice {(i*G+q)*4..+3}; a group of G
+// sequences is processed together and the G partial sums are combined by a shuffle reduce-scatter, after which lane q
+// owns sequence q (every lane evaluates the gates of a different (j, b)).
+// BPTT lane mapping: TWO outputs per thread and 2G lanes per output pair, so that every LDS.128 of the (3H long) dGH
+// vector feeds four FFMA2 instead of two -- the shared-memory pipe, not the FMA pipe, is what the 3x longer input vector
+// of the backward mat-vec saturates otherwise; the 2G partial sums of 2 outputs x G sequences are reduce-scattered over
+// the 2G lanes (each lane ends up owning one (k, b)).
+//
+// HBM traffic goes through shared memory in both directions: the per-step inputs (gi, or r,z,n,q,h_{t-1},dy) are
+// prefetched PF steps ahead with cp.async (16-byte pieces of coalesced 128/256-byte row segments) into a ring, the
+// outputs are staged and written as coalesced float4 rows right after the step's barrier.  Every thread owns a FIXED
+// set of at most two load and two store items whose addresses are computed once, so a step's I/O is a handful of
+// instructions (recomputing (sequence, array, column) from the thread index every step cost a third of the step in the
+// first version; a ninth, dedicated I/O warp was tried too: 288 threads are allocated like 384, which caps the compute
+// threads at 168 registers and spills the weight slices).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace {
+
+constexpr int CL_THREADS = 256;
+constexpr int CL_PF = 4;          // prefetch distance (timesteps) of the cp.async input ring
+constexpr int CL_HPAD = 16;       // state rows are H+16 floats apart (bank spread between the sequences of a lane group)
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t laddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank));
+  return r;
+}
+// 16-byte store into a cluster CTA's shared memory (own CTA included) that completes 16 bytes of that CTA's mbarrier
+__device__ __forceinline__ void st_async_v4(uint32_t raddr, float a, float b, float c, float d, uint32_t rbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1,%2,%3,%4}, [%5];" ::"r"(raddr),
+               "r"(__float_as_uint(a)), "r"(__float_as_uint(b)), "r"(__float_as_uint(c)), "r"(__float_as_uint(d)),
+               "r"(rbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_susp(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(0x989680u)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
+// reduce-scatter of N per-lane partials over N consecutive lanes: afterwards v[0] of lane q (q = lane % N) is the total
+// of index q
+template <int N>
+__device__ __forceinline__ void reduce_scatter(float (&v)[N], int q) {
+#pragma unroll
+  for (int s = N / 2; s >= 1; s >>= 1) {
+    const bool up = (q & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+}
+
+// =====================================================================================================================
+// forward
+// =====================================================================================================================
+struct ClFwdParams {
+  float* gi;         // (B,T,3H) in: x W_ih^T + b_ih ; out (if save): r,z,n
+  const float* whh;  // (3H,H)
+  const float* bhh;  // (3H)
+  float* y;          // (B,T,H)
+  float* q;          // (B,T,H) out (if save)
+  int B, T, save;
+};
+
+template <int H, int CS, int NGRP>
+struct ClFwdSmem {
+  static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
+  static constexpr int HBUF = 2 * BT * HR;             // floats
+  static constexpr int RING = CL_PF * BT * 3 * HU;     // floats
+  static constexpr int STG = 2 * BT * 5 * HU;          // floats
+  static constexpr size_t bytes = (size_t)(HBUF + RING + STG) * 4 + 128;
+};
+
+template <int H, int CS, int NGRP>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams p) {
+  using S = ClFwdSmem<H, CS, NGRP>;
+  constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR, KS = H / G;
+  static_assert(KS == 32, "96 weight registers per thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);            // [NGRP][2]
+  float* hbuf = reinterpret_cast<float*>(smem_raw + 128);            // [2][BT][HR]
+  float* ring = hbuf + S::HBUF;                                      // [PF][BT][3][HU]
+  float* stg = ring + S::RING;                                       // [2][BT][5][HU]
+  const int tid = threadIdx.x, jl = tid / G, ql = tid % G;
+  const uint32_t rank = cluster_ctarank();
+  const int j = (int)rank * HU + jl;
+  const int T = p.T;
+  const int b0 = (blockIdx.x / CS) * BT;
+  const bool save = p.save != 0;
+
+  for (int i = tid; i < S::HBUF + S::RING; i += CL_THREADS) hbuf[i] = 0.f;     // h_{-1} = 0; ring rows of absent sequences
+  constexpr uint32_t TXB = (uint32_t)(H * G * 4);                   // bytes one group receives per step
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_expect_tx(&bars[i], TXB);     // arm phase 0 of every barrier
+  }
+  __syncthreads();
+
+  // ---- this thread's share of the step's HBM traffic: fixed items, addresses computed once ----
+  constexpr int Q = HU / 4;                               // float4 per row segment
+  constexpr int NLI = BT * 3 * Q, NSI = BT * 5 * Q;       // load / store items per step
+  constexpr int NLD = (NLI + CL_THREADS - 1) / CL_THREADS, NSD = (NSI + CL_THREADS - 1) / CL_THREADS;
+  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * 3 * HU) * 4u, STG_BYTES = (uint32_t)(BT * 5 * HU) * 4u;
+  const float* lp[NLD]; uint32_t ls[NLD]; bool lv[NLD];
+#pragma unroll
+  for (int m = 0; m < NLD; ++m) {
+    const int n = tid + CL_THREADS * m, j4 = n % Q, g = (n / Q) % 3, b = n / (3 * Q);
+    lv[m] = (n < NLI) && (b0 + b < p.B);
+    lp[m] = p.gi + (size_t)(b0 + (lv[m] ? b : 0)) * T * (3 * H) + g * H + (int)rank * HU + j4 * 4;
+    ls[m] = smem_u32(ring) + (uint32_t)((b * 3 + g) * HU + j4 * 4) * 4u;
+  }
+  float* sp[NSD]; uint32_t ss[NSD]; bool sv[NSD]; int sst[NSD];
+#pragma unroll
+  for (int m = 0; m < NSD; ++m) {
+    const int n = tid + CL_THREADS * m, j4 = n % Q, wch = (n / Q) % 5, b = n / (5 * Q);
+    sv[m] = (n < NSI) && (b0 + b < p.B) && (save || wch == 4);
+    const size_t seq = (size_t)(b0 + (sv[m] ? b : 0)) * T;
+    float* base = (wch < 3) ? p.gi + seq * (3 * H) + wch * H : (wch == 3 ? p.q + seq * H : p.y + seq * H);
+    sp[m] = base + (int)rank * HU + j4 * 4;
+    sst[m] = (wch < 3) ? 3 * H : H;
+    ss[m] = smem_u32(stg) + (uint32_t)((b * 5 + wch) * HU + j4 * 4) * 4u;
+  }
+  auto prefetch = [&](int t) {
+    if (t < T) {
+      const uint32_t so = (uint32_t)(t % CL_PF) * SLOT_BYTES;
+#pragma unroll
+      for (int m = 0; m < NLD; ++m)
+        if (lv[m]) cp_async16(ls[m] + so, lp[m] + (size_t)t * (3 * H));
+    }
+    cp_async_commit();
+  };
+  auto store = [&](int t) {
+    const uint32_t so = (uint32_t)(t & 1) * STG_BYTES;
+#pragma unroll
+    for (int m = 0; m < NSD; ++m)
+      if (sv[m]) *reinterpret_cast<float4*>(sp[m] + (size_t)t * sst[m]) = lds_v4(ss[m] + so);
+  };
+  for (int t = 0; t < CL_PF - 1; ++t) prefetch(t);
+
+  // =============================== compute warps ===============================
+  // ---- W_hh slice into registers (float2 pairs for FFMA2) ----
+  float2 w[3][KS / 2];
+  float bh[3];
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    bh[g] = p.bhh[g * H + j];
+#pragma unroll
+    for (int i = 0; i < KS / 4; ++i) {
+      const float4 v = *reinterpret_cast<const float4*>(p.whh + (size_t)(g * H + j) * H + (i * G + ql) * 4);
+      w[g][2 * i] = make_float2(v.x, v.y);
+      w[g][2 * i + 1] = make_float2(v.z, v.w);
+    }
+  }
+  cluster_sync_all();      // every CTA's barriers are initialised and armed before anybody sends
+
+  // Senders: the lanes whose hidden unit is the first of a run of four (jl % 4 == 0) collect the run's values of THEIR
+  // sequence from the three sibling lanes (same ql, jl+1..3) and store 16 bytes into every CTA's state vector.
+  // The four lanes of a run all end up with the run's four values; lane i of the run serves the destination CTAs
+  // c == i (mod 4), so the stores to different CTAs leave in ONE warp instruction instead of CS consecutive ones.
+  const int lane = tid & 31;
+  const int src0 = lane & ~(3 * G);                 // lane of (first unit of the run, same sequence)
+  constexpr int ND = (CS + 3) / 4;                  // destinations per lane
+  uint32_t r_h[ND], r_bar[ND];
+  bool r_ok[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const int c = (jl & 3) + 4 * d;
+    r_ok[d] = c < CS;
+    r_h[d] = mapa_shared(smem_u32(hbuf + ql * HR + (j & ~3)), (uint32_t)(r_ok[d] ? c : 0));
+    r_bar[d] = mapa_shared(smem_u32(bars), (uint32_t)(r_ok[d] ? c : 0));
+  }
+  float hprev[NGRP];
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) hprev[g] = 0.f;
+  const uint32_t hbuf_a = smem_u32(hbuf);
+
+  for (int t = 0; t < T; ++t) {
+    cp_async_wait<CL_PF - 2>();          // this thread's share of step t's gi rows has landed
+    __syncthreads();                     // ... and everybody else's; also closes step t-1's staging writes
+    if (t > 0) store(t - 1);             // outputs of step t-1: coalesced float4 rows
+    prefetch(t + CL_PF - 1);
+    const int par = t & 1, ppar = par ^ 1;
+    float* sgw = stg + par * (BT * 5 * HU);
+#pragma unroll
+    for (int grp = 0; grp < NGRP; ++grp) {
+      // ---- wait for h_{t-1} of this group (all CTAs' slices) ----
+      if (t > 0) {
+        mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((t - 1) >> 1) & 1));
+        if (tid == 0 && t + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);   // re-arm for step t+1's values
+      }
+      const float* gr_ = ring + (((t % CL_PF) * BT + grp * G + ql) * 3) * HU + jl;
+      const float gr = gr_[0], gz = gr_[HU], gn = gr_[2 * HU];
+      float2 acc[G][3];
+#pragma unroll
+      for (int b = 0; b < G; ++b) {
+        acc[b][0] = make_float2((b == ql) ? bh[0] : 0.f, 0.f);
+        acc[b][1] = make_float2((b == ql) ? bh[1] : 0.f, 0.f);
+        acc[b][2] = make_float2(0.f, 0.f);
+      }
+      const uint32_t hc = hbuf_a + (uint32_t)((ppar * BT + grp * G) * HR) * 4u + 16u * (uint32_t)ql;
+#pragma unroll
+      for (int i = 0; i < KS / 4; ++i) {
+#pragma unroll
+        for (int b = 0; b < G; ++b) {
+          const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u);
+          const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            acc[b][g] = __ffma2_rn(w[g][2 * i], h01, acc[b][g]);
+            acc[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, acc[b][g]);
+          }
+        }
+      }
+      float own[3];
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        float v[G];
+#pragma unroll
+        for (int b = 0; b < G; ++b) v[b] = acc[b][g].x + acc[b][g].y;
+        reduce_scatter<G>(v, ql);
+        own[g] = v[0];
+      }
+      const float r = sigmoid_mufu(gr + own[0]);
+      const float z = sigmoid_mufu(gz + own[1]);
+      const float qv = own[2] + bh[2];
+      const float n = tanh_mufu(fmaf(r, qv, gn));
+      const float h = fmaf(z, hprev[grp] - n, n);
+      hprev[grp] = h;
+      // ---- all-gather: h_t[b][j] into every CTA's state vector (parity t&1), signalling that CTA's barrier ----
+      if (t + 1 < T) {
+        const uint32_t off = (uint32_t)((par * BT + grp * G) * HR) * 4u;
+        const float h0 = __shfl_sync(0xffffffffu, h, src0), h1 = __shfl_sync(0xffffffffu, h, src0 + G),
+                    h2 = __shfl_sync(0xffffffffu, h, src0 + 2 * G), h3 = __shfl_sync(0xffffffffu, h, src0 + 3 * G);
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          if (r_ok[d]) st_async_v4(r_h[d] + off, h0, h1, h2, h3, r_bar[d] + (uint32_t)(grp * 2 + par) * 8u);
+      }
+      float* so = sgw + ((grp * G + ql) * 5) * HU + jl;
+      so[0] = r; so[HU] = z; so[2 * HU] = n; so[3 * HU] = qv; so[4 * HU] = h;
+    }
+  }
+  __syncthreads();
+  store(T - 1);
+  cp_async_wait<0>();
+  cluster_sync_all();      // nobody leaves while a peer could still be writing into its shared memory
+}
+
+// =====================================================================================================================
+// BPTT
+// =====================================================================================================================
+struct ClBwdParams {
+  const float* dy;   // (B,T,H), or (B,H) when dy_last
+  const float* rzn;  // (B,T,3H)
+  const float* q;    // (B,T,H)
+  const float* y;    // (B,T,H): h_{t-1} is row t-1
+  const float* whh;  // (3H,H)
+  float* dgi;        // (B,T,3H) out: dar, daz, dan
+  float* dq;         // (B,T,H)  out: dan * r
+  int B, T, dy_last;
+};
+
+template <int H, int CS, int NGRP>
+struct ClBwdSmem {
+  static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
+  static constexpr int DBUF = 2 * BT * 3 * HR;         // floats: dGH vectors, double-buffered
+  static constexpr int RING = CL_PF * BT * 6 * HU;     // r,z,n,q,h_{t-1},dy
+  static constexpr int STG = 2 * BT * 4 * HU;          // dar,daz,dan,dq
+  static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
+};
+
+template <int H, int CS, int NGRP>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams p) {
+  using S = ClBwdSmem<H, CS, NGRP>;
+  constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR;
+  constexpr int L2 = 2 * G;            // lanes per output pair
+  constexpr int J = H / L2;            // j values per lane and gate
+  static_assert(J == 16, "96 weight registers per thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);            // [NGRP][2]
+  float* dbuf = reinterpret_cast<float*>(smem_raw + 128);            // [2][BT][3][HR]
+  float* ring = dbuf + S::DBUF;                                      // [PF][BT][6][HU]
+  float* stg = ring + S::RING;                                       // [2][BT][4][HU]
+  const int tid = threadIdx.x, kp = tid / L2, ql = tid % L2;
+  const uint32_t rank = cluster_ctarank();
+  const int T = p.T;
+  const int b0 = (blockIdx.x / CS) * BT;
+  const int ob = ql % G, oo = ql / G;              // the (sequence-in-group, output-of-the-pair) this lane finishes
+  const int kl = 2 * kp + oo;                      // its output column inside the CTA's slice
+  const int k = (int)rank * HU + kl;
+
+  for (int i = tid; i < S::DBUF + S::RING; i += CL_THREADS) dbuf[i] = 0.f;
+  constexpr uint32_t TXB = (uint32_t)(3 * H * G * 4);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_expect_tx(&bars[i], TXB);
+  }
+  __syncthreads();
+
+  // ---- this thread's share of the step's HBM traffic: fixed items, addresses computed once ----
+  // ring slot layout per (slot, b): [r | z | n | q | h_{t-1} | dy] x HU ; staging per (parity, b): [dar|daz|dan|dq] x HU
+  constexpr int Q = HU / 4;
+  constexpr int NLI = BT * 6 * Q, NSI = BT * 4 * Q;
+  constexpr int NLD = (NLI + CL_THREADS - 1) / CL_THREADS, NSD = (NSI + CL_THREADS - 1) / CL_THREADS;
+  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * 6 * HU) * 4u, STG_BYTES = (uint32_t)(BT * 4 * HU) * 4u;
+  const float* lp[NLD]; uint32_t ls[NLD]; bool lv[NLD]; int lst[NLD]; bool lshift[NLD];
+#pragma unroll
+  for (int m = 0; m < NLD; ++m) {
+    const int n = tid + CL_THREADS * m, j4 = n % Q, wch = (n / Q) % 6, b = n / (6 * Q);
+    lv[m] = (n < NLI) && (b0 + b < p.B) && !(wch == 5 && p.dy_last);
+    const size_t seq = (size_t)(b0 + (lv[m] ? b : 0)) * T;
+    const int col = (int)rank * HU + j4 * 4;
+    lshift[m] = wch == 4;                                  // h_{t-1}: row t-1 of y, nothing at t = 0
+    const float* base = (wch < 3) ? p.rzn + seq * (3 * H) + wch * H
+                        : (wch == 3 ? p.q + seq * H : (wch == 4 ? p.y + seq * H - H : p.q + seq * H));
+    if (wch == 5 && !p.dy_last) base = p.dy + seq * H;
+    lp[m] = base + col;
+    lst[m] = (wch < 3) ? 3 * H : H;
+    ls[m] = smem_u32(ring) + (uint32_t)((b * 6 + wch) * HU + j4 * 4) * 4u;
+  }
+  float* sp[NSD]; uint32_t ss[NSD]; bool sv[NSD]; int sst[NSD];
+#pragma unroll
+  for (int m = 0; m < NSD; ++m) {
+    const int n = tid + CL_THREADS * m, j4 = n % Q, wch = (n / Q) % 4, b = n / (4 * Q);
+    sv[m] = (n < NSI) && (b0 + b < p.B);
+    const size_t seq = (size_t)(b0 + (sv[m] ? b : 0)) * T;
+    sp[m] = ((wch < 3) ? p.dgi + seq * (3 * H) + wch * H : p.dq + seq * H) + (int)rank * HU + j4 * 4;
+    sst[m] = (wch < 3) ? 3 * H : H;
+    ss[m] = smem_u32(stg) + (uint32_t)((b * 4 + wch) * HU + j4 * 4) * 4u;
+  }
+  auto prefetch = [&](int t) {         // t counts down; t < 0: nothing to load
+    if (t >= 0) {
+      const uint32_t so = (uint32_t)(t % CL_PF) * SLOT_BYTES;
+#pragma unroll
+      for (int m = 0; m < NLD; ++m)
+        if (lv[m] && !(lshift[m] && t == 0)) cp_async16(ls[m] + so, lp[m] + (size_t)t * lst[m]);
+    }
+    cp_async_commit();
+  };
+  auto store = [&](int t, int s) {
+    const uint32_t so = (uint32_t)(s & 1) * STG_BYTES;
+#pragma unroll
+    for (int m = 0; m < NSD; ++m)
+      if (sv[m]) *reinterpret_cast<float4*>(sp[m] + (size_t)t * sst[m]) = lds_v4(ss[m] + so);
+  };
+  for (int s = 0; s < CL_PF - 1; ++s) prefetch(T - 1 - s);
+
+  // =============================== compute warps ===============================
+  // ---- W_hh^T slices: wt[o][g][m] = (W[gH+jj][k0+o], W[gH+jj+1][k0+o]),  jj = (i*L2+ql)*4 + 2*(m&1), i = m>>1 ----
+  float2 wt[2][3][J / 2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < J / 4; ++i) {
+        const int jj = (i * L2 + ql) * 4;
+        const int kk = (int)rank * HU + 2 * kp + o;
+        const float a0 = p.whh[(size_t)(g * H + jj + 0) * H + kk], a1 = p.whh[(size_t)(g * H + jj + 1) * H + kk];
+        const float a2 = p.whh[(size_t)(g * H + jj + 2) * H + kk], a3 = p.whh[(size_t)(g * H + jj + 3) * H + kk];
+        wt[o][g][2 * i] = make_float2(a0, a1);
+        wt[o][g][2 * i + 1] = make_float2(a2, a3);
+      }
+  cluster_sync_all();
+
+  // Senders: output columns come in runs of four consecutive kl = 2*kp + oo; the run of lane (kp, oo, ob) lives in the
+  // lanes ((kr + i) >> 1) * L2 + ((kr + i) & 1) * G + ob of the same warp (kr = first column of the run in the warp)
+  const int lane = tid & 31;
+  const int wbase = lane - (kp % (32 / L2)) * L2 - oo * G;          // lane of (first pair of the warp, oo = 0, same ob)
+  const int kr = (kl & ~3) - 2 * (kp - kp % (32 / L2));            // first column of the run, relative to the warp's
+  int srcl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) srcl[i] = wbase + ((kr + i) >> 1) * L2 + ((kr + i) & 1) * G;
+  // lane i of the run (kl & 3) serves the destination CTAs c == i (mod 4): one warp instruction covers four CTAs
+  constexpr int ND = (CS + 3) / 4;
+  uint32_t r_d[ND], r_bar[ND];
+  bool r_ok[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const int c = (kl & 3) + 4 * d;
+    r_ok[d] = c < CS;
+    r_d[d] = mapa_shared(smem_u32(dbuf + (ob * 3) * HR + (k & ~3)), (uint32_t)(r_ok[d] ? c : 0));
+    r_bar[d] = mapa_shared(smem_u32(bars), (uint32_t)(r_ok[d] ? c : 0));
+  }
+  float carry[NGRP];
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g)
+    carry[g] = (p.dy_last && (b0 + g * G + ob) < p.B) ? p.dy[(size_t)(b0 + g * G + ob) * H + k] : 0.f;
+  const uint32_t dbuf_a = smem_u32(dbuf);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = T - 1 - s;
+    cp_async_wait<CL_PF - 2>();
+    __syncthreads();
+    if (s > 0) store(t + 1, s - 1);      // outputs of step t+1
+    prefetch(t - (CL_PF - 1));
+    const int par = s & 1, ppar = par ^ 1;
+    float* sgw = stg + par * (BT * 4 * HU);
+#pragma unroll
+    for (int grp = 0; grp < NGRP; ++grp) {
+      // saved activations of (b, t, k): everything that does not depend on the carried dh first
+      const float* rg = ring + (((t % CL_PF) * BT + grp * G + ob) * 6) * HU + kl;
+      const float r = rg[0], z = rg[HU], n = rg[2 * HU], qv = rg[3 * HU], dyv = rg[5 * HU];
+      const float hp = (t == 0) ? 0.f : rg[4 * HU];          // h_{-1} = 0 (row -1 is never loaded; the slot is stale)
+      const float omz = 1.f - z;
+      const float fA = omz * fmaf(-n, n, 1.f);
+      const float fB = (hp - n) * (z * omz);
+      const float fC = qv * (r * (1.f - r));
+      // ---- W_hh^T dGH_{t+1}: wait for the all-gathered vector of the previous step ----
+      if (s > 0) {
+        mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((s - 1) >> 1) & 1));
+        if (tid == 0 && s + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);
+        float2 acc[G][2];
+#pragma unroll
+        for (int b = 0; b < G; ++b) acc[b][0] = acc[b][1] = make_float2(0.f, 0.f);
+        const uint32_t dc = dbuf_a + (uint32_t)((ppar * BT + grp * G) * 3 * HR) * 4u + 16u * (uint32_t)ql;
+#pragma unroll
+        for (int i = 0; i < J / 4; ++i)
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int b = 0; b < G; ++b) {
+              const float4 dv = lds_v4(dc + (uint32_t)((b * 3 + g) * HR) * 4u + (uint32_t)(i * L2) * 16u);
+              const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
+#pragma unroll
+              for (int o = 0; o < 2; ++o) {
+                acc[b][o] = __ffma2_rn(wt[o][g][2 * i], d01, acc[b][o]);
+                acc[b][o] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[b][o]);
+              }
+            }
+        float v[L2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o)
+#pragma unroll
+          for (int b = 0; b < G; ++b) v[o * G + b] = acc[b][o].x + acc[b][o].y;
+        reduce_scatter<L2>(v, ql);
+        carry[grp] += v[0];
+      }
+      const float dh = dyv + carry[grp];
+      const float dan = dh * fA;
+      const float daz = dh * fB;
+      const float dar = dan * fC;
+      const float dqv = dan * r;
+      carry[grp] = dh * z;            // the direct path dL/dh_{t-1} += dh * z; the mat-vec part is added next step
+      if (s + 1 < T) {
+        const uint32_t off = (uint32_t)((par * BT + grp * G) * 3 * HR) * 4u;
+        float vr[4], vz[4], vq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          vr[i] = __shfl_sync(0xffffffffu, dar, srcl[i]);
+          vz[i] = __shfl_sync(0xffffffffu, daz, srcl[i]);
+          vq[i] = __shfl_sync(0xffffffffu, dqv, srcl[i]);
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          if (r_ok[d]) {
+            const uint32_t bar = r_bar[d] + (uint32_t)(grp * 2 + par) * 8u;
+            st_async_v4(r_d[d] + off, vr[0], vr[1], vr[2], vr[3], bar);
+            st_async_v4(r_d[d] + off + (uint32_t)HR * 4u, vz[0], vz[1], vz[2], vz[3], bar);
+            st_async_v4(r_d[d] + off + 2u * (uint32_t)HR * 4u, vq[0], vq[1], vq[2], vq[3], bar);
+          }
+      }
+      float* so = sgw + ((grp * G + ob) * 4) * HU + kl;
+      so[0] = dar; so[HU] = daz; so[2 * HU] = dan; so[3 * HU] = dqv;
+    }
+  }
+  __syncthreads();
+  store(0, T - 1);
+  cp_async_wait<0>();
+  cluster_sync_all();
+}
+
+template <int H, int CS, int NGRP>
+int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
+  using S = ClFwdSmem<H, CS, NGRP>;
+  auto kern = gru_cl_fwd_kernel<H, CS, NGRP>;
+  TG_OPT_IN_SMEM(kern, "gru_cl_fwd");
+  const int clusters = (p.B + S::BT - 1) / S::BT;
+  kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
+  return tg_check_launch("gru_cl_fwd");
+}
+
+template <int H, int CS, int NGRP>
+int launch_cl_bwd(cudaStream_t st, const ClBwdParams& p) {
+  using S = ClBwdSmem<H, CS, NGRP>;
+  auto kern = gru_cl_bwd_kernel<H, CS, NGRP>;
+  TG_OPT_IN_SMEM(kern, "gru_cl_bwd");
+  const int clusters = (p.B + S::BT - 1) / S::BT;
+  kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
+  return tg_check_launch("gru_cl_bwd");
+}
+
+}  // namespace
+
+// Which (hidden size, batch, direction) the cluster kernels take -- chosen from measurements on a B200 (tools/probe_cluster.py,
+// profiles/r02_probe_cluster.log; T = 768, us per layer pass, cluster vs. the kernel it replaces):
+//   H = 128  forward   B <= 296: 784 vs 747 (gru_fwd.cu, 512 threads, BT = 2)  -> legacy;   B = 512: 1489 vs 1561 -> cluster
+//   H = 128  BPTT      B = 256: 1057 vs 1477,  B = 512: 2076 vs 2956                          -> cluster
+//   H = 256  forward   B = 128: 2841 vs 9381,  B = 256: 5513 vs 9413 (gru_bigh.cu, W_hh from L2) -> cluster
+//   H = 256  BPTT      B = 128: 4967 vs 7653 -> cluster;   B = 256 (two groups per cluster): 9281 vs 7690 -> gru_bigh.cu
+// Exact sizes only: the k-slices are compile-time register arrays.  TIMEGAN_B200_CLUSTER=0 disables them, =2 forces them
+// for every H = 128 / 256 launch (tests).
+bool tg_cluster_takes(int H, int B, bool backward) {
+  const int mode = tg_use_cluster();
+  if (mode == 0 || (H != 128 && H != 256)) return false;
+  if (mode == 2) return true;
+  const int sms = tg_num_sms();
+  if (H == 128) return backward || ((B + 3) / 4) * 2 > sms;
+  return !backward || ((B + 7) / 8) * 8 <= sms;
+}
+
+// Sequence groups per cluster: one group (G sequences) while every cluster is co-resident (one CTA per SM), two beyond.
+int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T, int H,
+                  int save) {
+  ClFwdParams p{gi, whh, bhh, y, q, B, T, save};
+  const int sms = tg_num_sms();
+  if (H == 128) {
+    const int clusters1 = (B + 3) / 4;
+    return (clusters1 * 2 <= sms) ? launch_cl_fwd<128, 2, 1>(st, p) : launch_cl_fwd<128, 2, 2>(st, p);
+  }
+  if (H == 256) {
+    const int clusters1 = (B + 7) / 8;
+    return (clusters1 * 8 <= sms) ? launch_cl_fwd<256, 8, 1>(st, p) : launch_cl_fwd<256, 8, 2>(st, p);
+  }
+  tg_set_error("gru_cl_fwd: hidden size %d not supported", H);
+  return TG_ERR_UNSUPPORTED;
+}
+
+int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y, const float* whh,
+                  float* dgi, float* dq, int B, int T, int H, int dy_last) {
+  ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
+  const int sms = tg_num_sms();
+  if (H == 128) {
+    const int clusters1 = (B + 3) / 4;
+    return (clusters1 * 2 <= sms) ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
+  }
+  if (H == 256) {
+    const int clusters1 = (B + 7) / 8;
+    return (clusters1 * 8 <= sms) ? launch_cl_bwd<256, 8, 1>(st, p) : launch_cl_bwd<256, 8, 2>(st, p);
+  }
+  tg_set_error("gru_cl_bwd: hidden size %d not supported", H);
+  return TG_ERR_UNSUPPORTED;
+}

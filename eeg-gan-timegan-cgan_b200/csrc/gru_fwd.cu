@@ -296,6 +296,9 @@ int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* b
   TG_REQUIRE(H <= 1024, TG_ERR_UNSUPPORTED, "gru_fwd: hidden size %d > 1024", H);
   const int save = (flags & TG_GRU_SAVE) ? 1 : 0;
   TG_REQUIRE(!save || q, TG_ERR_ARG, "gru_fwd: save requested without q buffer");
+  if (tg_cluster_takes(H, B, false) && !(flags & TG_GRU_NO_BULK) && tg_aligned16(gi) && tg_aligned16(y) && tg_aligned16(whh) &&
+      (!save || tg_aligned16(q)))
+    return tg_gru_cl_fwd(st, gi, whh, bhh, y, q, B, T, H, save);
   if (H > 128) return tg_bigh_fwd(st, gi, whh, bhh, y, q, B, T, H, save);
   FwdParams p{gi, whh, bhh, y, q, B, T, H, save, 0};
   p.bulk = (H % 4 == 0) && tg_aligned16(gi) && tg_aligned16(y) && (!save || tg_aligned16(q)) &&

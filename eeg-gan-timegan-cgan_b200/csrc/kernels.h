@@ -34,6 +34,15 @@ int tg_bigh_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, cons
                     const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh_t,
                     float* gib, float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only);
 
+// cluster kernels for H = 128 / 256 (gru_cluster.cu): W_hh split over the register files of 2 / 8 SMs, state
+// all-gathered through distributed shared memory every step
+bool tg_cluster_takes(int H, int B, bool backward);
+int tg_use_cluster();
+int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T, int H,
+                  int save);
+int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y, const float* whh,
+                  float* dgi, float* dq, int B, int T, int H, int dy_last);
+
 // time-batched contractions (FFMA baseline path; fp32 exact)
 int tg_gemm_nt_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
                     int ldc, int M, int N, int K, int accumulate);
@@ -59,6 +68,7 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
 int tg_max_optin_smem();
 int tg_gemm_smem_budget();
 int tg_long_chunks();
+int tg_bwd_pair();
 int tg_wgrad_cta_cap();
 int tg_peer_timeout_ms();
 

@@ -32,6 +32,19 @@ int tg_adam_multi_impl(cudaStream_t st, int n, float* const* params, const float
 int tg_snapshot_if_better_impl(cudaStream_t st, int n, float* const* dst, const float* const* src,
                                const long long* sizes, const float* value, float* best, float* best_step, float step);
 
+// fused discriminator head (head.cu)
+int tg_head_fwd_impl(cudaStream_t st, const float* yl, long long ld, int B, int H, int n_half, const float* w,
+                     const float* bias, float* u, float* v, int training, const float* labels, float* wbar, float* uv,
+                     float* sigma, float* p, float* stats);
+int tg_head_seed_impl(cudaStream_t st, const float* p, const float* labels, const float* wbar, const float* stats,
+                      float* scal, float* seed, float* gyf, int B, int H, float Bg, float target, float band);
+int tg_head_bwd_impl(cudaStream_t st, const float* yl, long long ld, const float* hd, long long ld_hd, const float* p,
+                     const float* labels, const float* w, const float* wbar, const float* uv, const float* sigma,
+                     const float* scal, const float* r1, float* gyr, float* ghd, float* gw, float* gb, float* loss_val,
+                     int B, int H, float Bg, float gamma);
+int tg_head_adv_bwd_impl(cudaStream_t st, const float* p, const float* wbar, const float* gout, float* gy, int B, int H,
+                         float Bg);
+
 // rng
 int tg_rng_uniform_impl(cudaStream_t st, float* out, long long n, unsigned long long seed, unsigned long long offset,
                         float lo, float hi, const unsigned long long* ctr);

@@ -8,8 +8,11 @@
 //               (2-D tensor maps, 128-byte swizzle, K padded to 32-float blocks by TMA zero fill)
 //   warp 1      TMEM allocation + single-thread tcgen05.mma issue, kind::tf32, fp32 accumulators in TMEM
 //               (double-buffered: 2 x NT columns), tcgen05.commit releases smem stages / publishes accumulators
-//   warps 2-5   epilogue: tcgen05.ld (one accumulator row per thread) -> per-warp smem transpose -> + bias ->
-//               coalesced 128-byte row segments to global
+//   warps 2-5   epilogue: tcgen05.ld (one accumulator row per thread, 32 columns per instruction, the next chunk's load
+//               in flight while this one is stored) -> + bias (staged in shared memory once) -> 128B-swizzled 32x32
+//               staging tile -> TMA store (cp.async.bulk.tensor), double-buffered per warp: no thread ever issues a
+//               global store, and rows / columns beyond M / N are clipped by the tensor map.
+//               (accumulate mode, unused by the training step, keeps the read-modify-write path through the LSU)
 //   warps 6-9   (3-pass mode only) split each landed tile in place into TF32-exact hi and residual lo parts
 // Two precisions:
 //   passes = 1  plain TF32 operands (10-bit mantissa; the "bf16-class" 2e-2 projection mode)
@@ -25,7 +28,8 @@ constexpr int BM = 128;           // rows per tile = UMMA M
 constexpr int KBLK = 32;          // fp32 per 128-byte swizzle row
 constexpr int A_BLK_BYTES = BM * 128;
 constexpr int NUM_THREADS_1P = 192, NUM_THREADS_3P = 320;
-constexpr int TAIL_BYTES = 512 + 4 * 32 * 36 * 4;   // barriers + epilogue staging
+constexpr int STG_BYTES = 2 * 4096;                  // per epilogue warp: two 32-row x 128-byte staging tiles
+constexpr int TAIL_BYTES = 2048 + 4 * STG_BYTES;     // barriers (512) + bias (<= 256 floats) + pad | epilogue staging
 
 struct TcParams {
   float* C;
@@ -40,7 +44,8 @@ struct TcParams {
 
 template <int PASSES>
 __global__ void __launch_bounds__(PASSES == 3 ? NUM_THREADS_3P : NUM_THREADS_1P, 1)
-tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, TcParams p) {
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmC, TcParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NT = p.NT, KB = p.KB, NS = p.nstage;
@@ -61,7 +66,8 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* acc_full = w_full + 2;       // [2] MMA -> epilogue
   uint64_t* acc_empty = w_full + 4;      // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 6);
-  float* stg_base = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);   // 4 x [32][36] floats
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 512);     // [NT] (zeros if none)
+  unsigned char* stg_all = reinterpret_cast<unsigned char*>(bars) + 2048;                     // 4 x STG_BYTES, 1 KB aligned
 
   const int n0 = blockIdx.y * NT;
   const int num_tiles = (p.M + BM - 1) / BM;
@@ -73,7 +79,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 128); }
     mbar_fence_init();
   }
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmC); }
+  for (int i = threadIdx.x; i < NT; i += blockDim.x)
+    bias_s[i] = (p.bias && blockIdx.y * NT + i < p.N) ? p.bias[blockIdx.y * NT + i] : 0.f;
   if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
@@ -141,8 +149,9 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp < 6) {
     // ===================== epilogue (warps 2..5 -> TMEM lane quarters 2,3,0,1) =====================
     const int quarter = warp & 3;
-    float* stg = stg_base + (warp - 2) * (32 * 36);
+    unsigned char* stg = stg_all + (warp - 2) * STG_BYTES;
     int it = 0;
+    uint32_t nstore = 0;     // TMA stores issued by this warp (staging buffer = nstore & 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (uint32_t)((it >> 1) & 1);
@@ -150,42 +159,75 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NT);
       const long long row0 = (long long)tile * BM + quarter * 32;   // first row of this warp's 32-row slab
-      const int c4 = lane & 7, rsub = lane >> 3;
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        // TMEM -> registers: lane = accumulator row, 32 consecutive columns
-        float v[32];
-        tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<float(*)[16]>(&v[0]));
-        if (c0 + 16 < NT) tmem_ld16(taddr + (uint32_t)(c0 + 16), *reinterpret_cast<float(*)[16]>(&v[16]));
-        // registers -> per-warp staging tile [32 rows][36 floats] (conflict-free 16-B accesses both ways)
+      if (!p.accumulate) {
+        // ---- TMA-store path ----
+        uint32_t ra[32];
+        tmem_ld32_issue(taddr, ra);
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          float v[32];
+          tmem_ld_wait();
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          *reinterpret_cast<float4*>(stg + lane * 36 + q4 * 4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-        __syncwarp();
-        // staging -> global, transposed: 8 lanes cover one 128-byte row segment, 4 rows per instruction
-        const int n = n0 + c0 + c4 * 4;
-        const bool col_ok = (c0 + c4 * 4 < NT) && (n + 3 < p.N);
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias && col_ok) bv = *reinterpret_cast<const float4*>(p.bias + n);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(ra[i]);
+          if (c0 + 32 < NT) tmem_ld32_issue(taddr + (uint32_t)(c0 + 32), ra);   // next chunk in flight during the store
+          unsigned char* buf = stg + (nstore & 1u) * 4096;
+          if (lane == 0) bulk_wait_read<1>();     // the store that last read this buffer (two stores ago) is done
+          __syncwarp();
+          const uint32_t rowa = smem_u32(buf) + (uint32_t)lane * 128u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = rsub + 4 * i;
-          const long long row = row0 + r;
-          if (col_ok && row < p.M) {
-            float4 o = *reinterpret_cast<const float4*>(stg + r * 36 + c4 * 4);
-            o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-            float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + n);
-            if (p.accumulate) {
-              const float4 old = *dst;
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            *dst = o;
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * j);   // broadcast read
+            const uint32_t dst = rowa + (uint32_t)((j ^ (lane & 7)) << 4);             // 128-byte swizzle
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "f"(v[4 * j] + bv.x),
+                         "f"(v[4 * j + 1] + bv.y), "f"(v[4 * j + 2] + bv.z), "f"(v[4 * j + 3] + bv.w)
+                         : "memory");
           }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0 && row0 < p.M && n0 + c0 < p.N) {
+            tma_store_2d(&tmC, buf, n0 + c0, (int)row0);
+            bulk_commit();
+          } else if (lane == 0) {
+            bulk_commit();                        // keep the group count in step with nstore
+          }
+          ++nstore;
         }
+      } else {
+        // ---- read-modify-write path (C += ...): staging tile [32 rows][36 floats], coalesced 128-byte row segments ----
+        float* stf = reinterpret_cast<float*>(stg);
+        if (lane == 0) bulk_wait_read<0>();
         __syncwarp();
+        const int c4 = lane & 7, rsub = lane >> 3;
+        for (int c0 = 0; c0 < NT; c0 += 32) {
+          float v[32];
+          tmem_ld16(taddr + (uint32_t)c0, *reinterpret_cast<float(*)[16]>(&v[0]));
+          if (c0 + 16 < NT) tmem_ld16(taddr + (uint32_t)(c0 + 16), *reinterpret_cast<float(*)[16]>(&v[16]));
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4)
+            *reinterpret_cast<float4*>(stf + lane * 36 + q4 * 4) = make_float4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+          __syncwarp();
+          const int n = n0 + c0 + c4 * 4;
+          const bool col_ok = (c0 + c4 * 4 < NT) && (n + 3 < p.N);
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok) bv = *reinterpret_cast<const float4*>(bias_s + c0 + c4 * 4);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = rsub + 4 * i;
+            const long long row = row0 + r;
+            if (col_ok && row < p.M) {
+              float4 o = *reinterpret_cast<const float4*>(stf + r * 36 + c4 * 4);
+              float4* dst = reinterpret_cast<float4*>(p.C + row * p.ldc + n);
+              const float4 old = *dst;
+              o.x += bv.x + old.x; o.y += bv.y + old.y; o.z += bv.z + old.z; o.w += bv.w + old.w;
+              *dst = o;
+            }
+          }
+          __syncwarp();
+        }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[as]);
     }
+    if (lane == 0) bulk_wait_all<0>();       // every TMA store of this warp has landed before the CTA exits
   } else {
     // ===================== TF32 hi/lo splitter (3-pass mode, warps 6..9) =====================
     if (PASSES == 3) {
@@ -253,23 +295,29 @@ int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, in
   const int n_pad = (N + 15) / 16 * 16;
   const int copies = (passes == 3) ? 2 : 1;
   const int stage_bytes = copies * A_BLK_BYTES;
-  // widest n-tile (<= 256 columns) whose resident W copy leaves room for >= 3 ring stages
+  // widest n-tile (<= 256 columns) whose resident W copy leaves room for >= 3 ring stages (2 when K >= 256: the
+  // resident W of a 32-column tile alone is 64 KB there).  With more than one n-tile NT is a multiple of 32, the width
+  // of the epilogue's store boxes: a box must never reach into the neighbouring tile's columns.
   int n_tiles = (n_pad + 255) / 256, NT = 0, w_total = 0, nstage = 0;
-  for (; n_tiles <= 16; ++n_tiles) {
-    NT = ((n_pad + n_tiles - 1) / n_tiles + 15) / 16 * 16;
+  for (; n_tiles <= 24; ++n_tiles) {
+    NT = (n_pad + n_tiles - 1) / n_tiles;
+    NT = (n_tiles > 1) ? (NT + 31) / 32 * 32 : (NT + 15) / 16 * 16;
     w_total = ((copies * KB * NT * 128) + 1023) / 1024 * 1024;
-    nstage = (tg_gemm_smem_budget() - 2048 - w_total - TAIL_BYTES) / stage_bytes;
-    if (nstage >= 3) break;
+    nstage = (tg_gemm_smem_budget() - 1024 - w_total - TAIL_BYTES) / stage_bytes;
+    if (nstage >= 3 || (KB >= 8 && nstage >= 2)) break;
   }
+  n_tiles = (n_pad + NT - 1) / NT;      // rounding NT up may have made the last tile(s) unnecessary
   if (nstage > 8) nstage = 8;
-  if (nstage < 3) { tg_set_error("proj_tc: tile does not fit shared memory (K=%d N=%d passes=%d)", K, N, passes); return TG_ERR_UNSUPPORTED; }
+  if (nstage < 2 || (nstage < 3 && KB < 8)) { tg_set_error("proj_tc: tile does not fit shared memory (K=%d N=%d passes=%d)", K, N, passes); return TG_ERR_UNSUPPORTED; }
   const size_t smem = (size_t)w_total + (size_t)nstage * stage_bytes + TAIL_BYTES;
 
-  alignas(64) CUtensorMap tmA, tmW;
+  alignas(64) CUtensorMap tmA, tmW, tmC;
   if (tg_make_map_2d(&tmA, A, M, K, lda, KBLK, BM) != TG_OK) return TG_ERR_UNSUPPORTED;
   if (tg_make_map_2d(&tmW, W, N, K, ldw, KBLK, NT) != TG_OK) return TG_ERR_UNSUPPORTED;
+  if (tg_make_map_2d(&tmC, C, M, N, ldc, 32, 32) != TG_OK) return TG_ERR_UNSUPPORTED;   // output: 32 x 32 store boxes
 
-  TcParams p{C, bias, ldc, M, N, K, NT, KB, nstage, accumulate, pow2_at_least(2 * NT)};
+  // the epilogue reads the accumulator in 32-column chunks: the last chunk of buffer 1 may reach past 2*NT
+  TcParams p{C, bias, ldc, M, N, K, NT, KB, nstage, accumulate, pow2_at_least(NT + (NT + 31) / 32 * 32)};
   const int num_tiles = (M + BM - 1) / BM;
   int gx = tg_num_sms() / n_tiles;
   if (gx > num_tiles) gx = num_tiles;
@@ -277,10 +325,10 @@ int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, in
   dim3 grid(gx, n_tiles);
   if (passes == 3) {
     TG_OPT_IN_SMEM(tc_gemm_tn_kernel<3>, "proj_tc");
-    tc_gemm_tn_kernel<3><<<grid, NUM_THREADS_3P, smem, st>>>(tmA, tmW, p);
+    tc_gemm_tn_kernel<3><<<grid, NUM_THREADS_3P, smem, st>>>(tmA, tmW, tmC, p);
   } else {
     TG_OPT_IN_SMEM(tc_gemm_tn_kernel<1>, "proj_tc");
-    tc_gemm_tn_kernel<1><<<grid, NUM_THREADS_1P, smem, st>>>(tmA, tmW, p);
+    tc_gemm_tn_kernel<1><<<grid, NUM_THREADS_1P, smem, st>>>(tmA, tmW, tmC, p);
   }
   return tg_check_launch("proj_tc");
 }

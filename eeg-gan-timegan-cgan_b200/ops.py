@@ -103,15 +103,27 @@ class _WgradSide:
 
 class LayerSave:
     """Activations one layer keeps for its backward pass (all (B,T,*) fp32, contiguous)."""
-    __slots__ = ("inp", "rzn", "q", "y")
+    __slots__ = ("inp", "rzn", "q", "y", "ipad")
 
-    def __init__(self, inp, rzn, q, y):
-        self.inp, self.rzn, self.q, self.y = inp, rzn, q, y
+    def __init__(self, inp, rzn, q, y, ipad: int = 0):
+        # ipad > 0: `inp` carries that many zero columns on the right (see pad_cols)
+        self.inp, self.rzn, self.q, self.y, self.ipad = inp, rzn, q, y, ipad
 
     def narrow(self, start: int, length: int) -> "LayerSave":
         """Batch slice [start, start+length) as views (contiguous: the batch is the leading dimension)."""
         f = lambda t: t.narrow(0, start, length)
-        return LayerSave(f(self.inp), f(self.rzn), f(self.q), f(self.y))
+        return LayerSave(f(self.inp), f(self.rzn), f(self.q), f(self.y), self.ipad)
+
+
+def pad_cols(t: torch.Tensor, mult: int = 4) -> Tuple[torch.Tensor, int]:
+    """Zero-pad the last dimension to a multiple of `mult` floats.  The tensor-core tiles are fed by TMA, whose rows
+    must be 16-byte multiples: the 14 EEG channels (a 56-byte pitch) are carried as 16 -- two zero columns that add
+    nothing to any contraction -- instead of sending every 14-wide GEMM to the FFMA fallback."""
+    k = t.shape[-1]
+    pad = (-k) % mult
+    if pad == 0:
+        return t, 0
+    return torch.nn.functional.pad(t, (0, pad)), pad
 
 
 def _ws(nbytes: int, device) -> torch.Tensor:
@@ -212,13 +224,17 @@ def stack_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], save: bool,
         w_ih, w_hh, b_ih, b_hh = _layer_weights(weights, l)
         H = w_hh.shape[1]
         gi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=x.device)
+        ipad = 0
+        if inp.shape[-1] % 4 != 0 and _PROJ_MODE != _lib.PROJ_FP32 and B * T >= 128:
+            inp, ipad = pad_cols(inp)               # (B,T,14) -> (B,T,16): layer 0 of the embedder
+            w_ih, _ = pad_cols(w_ih)
         proj(inp.view(B * T, -1), w_ih, b_ih, gi.view(B * T, 3 * H))
         y = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
         q = torch.empty(B, T, H, dtype=torch.float32, device=x.device) if save else None
         check(lib.tg_gru_fwd(stream_ptr(), ptr(gi), ptr(w_hh), ptr(b_hh), ptr(y), ptr(q), B, T, H,
                              _flags(_lib.GRU_SAVE if save else 0)), "tg_gru_fwd")
         if save:
-            saves.append(LayerSave(inp, gi, q, y))
+            saves.append(LayerSave(inp, gi, q, y, ipad))
         inp = y
         if masks is not None and l < L - 1:
             inp = y * masks[l]
@@ -247,6 +263,7 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
         w_ih, w_hh, _, _ = _layer_weights(weights, l)
         H = w_hh.shape[1]
         I = w_ih.shape[1]
+        Ip = I + sv.ipad              # width of the saved (zero-padded) layer input
         dgi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
         dq = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         w_hh_t = w_hh.t().contiguous() if H > 128 else None      # the H > 128 fallback walks W_hh^T rows
@@ -255,15 +272,33 @@ def stack_backward(dy: torch.Tensor, saves: List[LayerSave], weights: Sequence[t
         last_only = False
         dgi2 = dgi.view(B * T, 3 * H)
         if l > 0 or need_dx:          # the critical path first: dX feeds the next layer's BPTT
-            dx = torch.empty(B, T, I, dtype=torch.float32, device=dev)
-            dgrad(dgi2, w_ih, dx.view(B * T, I))
+            if sv.ipad:
+                dxp = torch.empty(B, T, Ip, dtype=torch.float32, device=dev)
+                dgrad(dgi2, pad_cols(w_ih)[0], dxp.view(B * T, Ip))
+                dx = dxp[..., :I].contiguous()
+            else:
+                dx = torch.empty(B, T, I, dtype=torch.float32, device=dev)
+                dgrad(dgi2, w_ih, dx.view(B * T, I))
             d = dx
             if masks is not None and l > 0:
                 d = dx * masks[l - 1]
         if need_dw:
             g_wih, g_whh, g_bih, g_bhh = _layer_weights(grads, l)
-            x2 = sv.inp.reshape(B * T, I)
-            side.issue(lambda: wgrad_gru(dgi, dq, x2, sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate), dgi, dq, x2)
+            x2 = sv.inp.reshape(B * T, Ip)
+            if sv.ipad:
+                def _wg_padded(dgi=dgi, dq=dq, x2=x2, sv=sv, g_wih=g_wih, g_whh=g_whh, g_bih=g_bih, g_bhh=g_bhh):
+                    # dW_ih against the padded input (the two extra columns come out as exact zeros and are dropped);
+                    # with accumulate the kernel adds onto its output, so the scratch starts at zero
+                    alloc = torch.zeros if accumulate else torch.empty
+                    tmp = alloc(g_wih.shape[0], x2.shape[1], dtype=torch.float32, device=dev)
+                    wgrad_gru(dgi, dq, x2, sv.y, tmp, g_whh, g_bih, g_bhh, accumulate)
+                    if accumulate:
+                        g_wih.add_(tmp[:, :g_wih.shape[1]])
+                    else:
+                        g_wih.copy_(tmp[:, :g_wih.shape[1]])
+                side.issue(_wg_padded, dgi, dq, x2)
+            else:
+                side.issue(lambda: wgrad_gru(dgi, dq, x2, sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate), dgi, dq, x2)
     side.join()
     return (dx if need_dx else None), grads
 
@@ -399,32 +434,54 @@ class GRUStackFunction(torch.autograd.Function):
 
 
 class LinearFunction(torch.autograd.Function):
-    """y = x W^T + b over the last dim (timegan_model.py:53 Recovery.out; :66/:79 G/S proj when h != z)."""
+    """y = x W^T + b over the last dim (timegan_model.py:53 Recovery.out; :66/:79 G/S proj when h != z).
+
+    A head whose width is not a multiple of 4 floats (Recovery.out: 14 channels) is evaluated 16 wide -- W and b
+    zero-padded, the two extra output columns dropped -- so that forward, dX and dW all run on the TMA-fed
+    tensor-core tiles (3xTF32, fp32 parity) instead of the FFMA fallback."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         require_cuda(x, "Linear input")
         x = x.contiguous()
         K = x.shape[-1]
+        N = weight.shape[0]
         x2 = x.view(-1, K)
-        out = proj(x2, weight.detach(), None if bias is None else bias.detach(), mode=_lib.PROJ_FP32)
+        tc = _PROJ_MODE != _lib.PROJ_FP32 and x2.shape[0] >= 128 and K % 4 == 0
+        mode = _lib.PROJ_TF32X3 if tc else _lib.PROJ_FP32     # heads always in fp32-parity precision
+        w, b = weight.detach(), (None if bias is None else bias.detach())
+        npad = (-N) % 4 if tc else 0
+        if npad:
+            w = torch.nn.functional.pad(w, (0, 0, 0, npad))
+            b = None if b is None else torch.nn.functional.pad(b, (0, npad))
+        out = proj(x2, w, b, mode=mode)
         ctx.save_for_backward(x2, weight)
-        ctx.has_bias = bias is not None
-        return out.view(*x.shape[:-1], weight.shape[0])
+        ctx.has_bias, ctx.npad, ctx.mode = bias is not None, npad, mode
+        out = out.view(*x.shape[:-1], N + npad)
+        return out[..., :N] if npad else out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
         x2, weight = ctx.saved_tensors
         N, K = weight.shape
-        d2 = dout.contiguous().view(-1, N)
+        npad = ctx.npad
+        d2 = dout.reshape(-1, N)
+        if npad:
+            d2 = torch.nn.functional.pad(d2, (0, npad))                  # (M, N) -> (M, N+npad), zeros on the right
+            wp = torch.nn.functional.pad(weight.detach(), (0, 0, 0, npad))
+        else:
+            d2 = d2.contiguous()
+            wp = weight.detach()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = dgrad(d2, weight.detach()).view(*dout.shape[:-1], K)
+            dx = dgrad(d2, wp).view(*dout.shape[:-1], K)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty_like(weight)
-            db = torch.empty(N, dtype=torch.float32, device=weight.device) if ctx.has_bias else None
-            wgrad(d2, x2, dw, db, N)
+            dwp = torch.empty(N + npad, K, dtype=torch.float32, device=weight.device)
+            dbp = torch.empty(N + npad, dtype=torch.float32, device=weight.device) if ctx.has_bias else None
+            wgrad(d2, x2, dwp, dbp, N + npad, mode=ctx.mode)
+            dw = dwp[:N].contiguous() if npad else dwp
+            db = None if dbp is None else (dbp[:N].contiguous() if npad else dbp)
         return dx, dw, db
 
 

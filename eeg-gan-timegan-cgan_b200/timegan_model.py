@@ -186,6 +186,13 @@ class Discriminator(nn.Module):
         last, _ = self.rnn.rnn(h, last_only=True, frozen=frozen)
         return self.head(last, frozen)
 
+    def adv_loss(self, h):
+        """bce(self(h), ones) with this network's weights as constants (gen_step, train_timegan.py:240-241): the GRU
+        stack keeps only its last step, and head + sigmoid + BCE (+ their backward) are one fused kernel each."""
+        from . import head as _head
+        last, _ = self.rnn.rnn(h, last_only=True, frozen=True)
+        return _head.adv_loss(self, last)
+
 
 class TimeGAN(nn.Module):
     """Bundle of submodules + convenience calls (timegan_model.py:101-118)."""

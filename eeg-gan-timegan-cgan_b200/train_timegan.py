@@ -31,6 +31,7 @@ import torch.optim as optim
 from torch.utils.data import DataLoader, TensorDataset
 
 from . import dist as _dist
+from . import head as _head
 from . import losses as _losses
 from . import noise as _noise
 from . import ops
@@ -531,64 +532,46 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
         y_real, y_fake = smooth_labels(B, label_smooth, device, nz)                  # tt:188
         masks = gru.dropout_masks(h_in)
         y_all, saves = ops.stack_forward(h_in, wd, save=True, masks=masks)
-        last = y_all[:, -1, :]
-    yl_r = last[:B].clone().requires_grad_(True)
-    yl_f = last[B:].clone().requires_grad_(True)
-    wbar_r = D.sn_weight()                                                           # power iteration 1 (tt:192)
-    d_real = torch.sigmoid(torch.nn.functional.linear(yl_r, wbar_r, D.fc.bias))
-    d_fake = D.head(yl_f)                                                            # power iteration 2 (tt:193)
+        last = y_all[:, -1, :]                       # (2B,H) view: row stride T*H, read in place by the head kernels
+        H = last.shape[1]
 
-    loss_bce = 0.5 * (bce(d_real, y_real) + bce(d_fake, y_fake))                    # tt:196
-    Bg = _dist.global_count(B)
-
-    r1 = None
-    obj = loss_bce
-    if r1_gamma > 0.0:                                                               # tt:199-202
-        saves_r = [sv.narrow(0, B) for sv in saves]
-        masks_r = None if masks is None else [m[:B] for m in masks]
-        seed = torch.autograd.grad(d_real.sum(), yl_r, retain_graph=True)[0]
-        with torch.no_grad():
-            v, _ = ops.stack_backward(seed, saves_r, wd, need_dx=True, need_dw=False, dy_last=True, masks=masks_r)
-            r1 = _dist.global_mean(_losses.sumsq(v), B)
-            ydot, tsaves = ops.stack_jvp_forward(v, saves_r, wd, masks=masks_r)
-        hd_last = ydot[:, -1, :].clone().requires_grad_(True)
-        sdot = (d_real * (1.0 - d_real) * torch.nn.functional.linear(hd_last, wbar_r)).sum()
-        obj = obj + (r1_gamma / Bg) * sdot          # d(0.5*gamma*r1)/dtheta = (gamma/B) d(sdot)/dtheta
-
-    with torch.no_grad():                                                            # tt:205-215
-        acc_real = _dist.global_mean((d_real > 0.5).float().sum(), B)
-        acc_fake = _dist.global_mean((d_fake < 0.5).float().sum(), B)
-        acc = 0.5 * (acc_real + acc_fake)
-        if band > 0:
-            scale = torch.clamp(1.0 - torch.clamp(acc - target_acc, min=0.0) / band, min=0.2)
-        else:
-            scale = torch.ones((), device=device)
-        loss_val = loss_bce.detach() + (0.5 * r1_gamma * r1 if r1 is not None else 0.0)
-        loss_val = loss_val * scale
-
-    head_params = [D.fc.weight_orig, D.fc.bias]
-    if r1 is not None:
-        gyr, gyf, ghd, gw, gb = torch.autograd.grad(obj * scale, [yl_r, yl_f, hd_last] + head_params)
-    else:
-        gyr, gyf, gw, gb = torch.autograd.grad(obj * scale, [yl_r, yl_f] + head_params)
-
-    with torch.no_grad():
+        # head forward (tm:96-98 for both calls, tt:196 BCE sums, tt:205-208 accuracy counts): ONE kernel; the legacy
+        # spectral-norm hook's two power iterations (one per D call) update fc.weight_u / fc.weight_v in place
+        hs = _head.forward(D, last, torch.cat([y_real.reshape(-1), y_fake.reshape(-1)]), 2)
+        stats, _ = _dist.allreduce_stats(hs.stats, B)          # data parallel: the sums of the global batch
+        Bg = _dist.global_count(B)
+        # throttle scale (tt:209-215) on the device, the R1 seed d(sum d_real)/d y_last (tt:200) and the fake half's
+        # input gradient (it needs nothing else, so its BPTT starts right away, beside the whole R1 chain)
+        scal, seed, gyf = _head.seed(hs, stats, Bg, target_acc, band, need_seed=r1_gamma > 0.0)
         grads = ops.alloc_like_flat(wd)
-        if r1 is not None:
+        r1 = None
+        if r1_gamma > 0.0:                                                           # tt:199-202
+            saves_r = [sv.narrow(0, B) for sv in saves]
+            masks_r = None if masks is None else [m[:B] for m in masks]
             saves_f = [sv.narrow(B, B) for sv in saves]
             masks_f = None if masks is None else [m[B:] for m in masks]
             grads_f = ops.alloc_like_flat(wd)
             fork_f = _Fork(device, 0)
-            with fork_f:                                   # BPTT of the fake half || reverse-over-tangent of the real half
+            with fork_f:                           # BPTT of the fake half || (dX-only BPTT -> tangent forward -> reverse)
                 ops.stack_backward(gyf, saves_f, wd, need_dx=False, need_dw=True, dy_last=True, grads=grads_f,
                                    accumulate=False, masks=masks_f)
+            v, _ = ops.stack_backward(seed, saves_r, wd, need_dx=True, need_dw=False, dy_last=True, masks=masks_r)
+            r1 = _dist.global_mean(_losses.sumsq(v), B)
+            ydot, tsaves = ops.stack_jvp_forward(v, saves_r, wd, masks=masks_r)
+            hd_last = ydot[:, -1, :]
+            # d(scale * (loss_bce + 0.5*gamma*r1))/d{y_last(real), tangent, fc}: 0.5*gamma*r1 enters through
+            # (gamma/Bg) * sdot, sdot = sum_b p(1-p) (hd_b . wbar)   
+            gyr, ghd, gw, gb, loss_val = _head.backward(D, hs, last, hd_last, scal, r1, Bg, r1_gamma)
             grads.flat.zero_()            # one launch for the whole stack (the buffers are views of one allocation)
             ops.stack_jvp_backward(gyr, ghd, saves_r, tsaves, wd, grads, accumulate=True, masks=masks_r)
             fork_f.join()
             grads.flat.add_(grads_f.flat)
         else:
+            gyr, _, gw, gb, loss_val = _head.backward(D, hs, last, None, scal, None, Bg, 0.0)
             ops.stack_backward(torch.cat([gyr, gyf], 0), saves, wd, need_dx=False, need_dw=True, dy_last=True,
                                grads=grads, accumulate=False, masks=masks)
+        acc = scal[1]
+        loss_val = loss_val.reshape(())
     _zero_grads(optD)                                                                # tt:218-221
     for p, g in zip(gru.layer_weights(), grads):
         p.grad = g
@@ -626,8 +609,7 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
         if gamma_cov > 0 or gamma_acf > 0:                                           # tt:254-263
             cov_term, acf_term = _losses.cov_acf_losses(x_hat, x, acf_max_lag, need_cov=gamma_cov > 0,
                                                         need_acf=gamma_acf > 0)
-    d_fake = model.discriminator(d_in, frozen=True)
-    g_adv = bce(d_fake, torch.ones_like(d_fake))
+    g_adv = model.discriminator.adv_loss(d_in)       # bce(D(d_in), ones) with D frozen: one head kernel (tt:240-241)
     g_sup = sup_loss_fake(h_hat)                                                     # tt:244
     fork_rec.join()
     fork_dec.join()

@@ -153,6 +153,29 @@ int tg_adam(void* stream, int n, float* const* params, const float* const* grads
             float* dev_state /* NULL, or device float[4] {lr, step, -, -}: the step counter and bias corrections
                                 then live on the device (CUDA-graph replay); `lr`/`step` arguments are ignored */);
 
+/* ---- fused discriminator head (timegan_model.py:92-98 spectral_norm(Linear(h,1)) + sigmoid; train_timegan.py:70 BCELoss,
+ *      :196 loss, :199-202 R1 seed / sdot term, :205-215 accuracy + throttle, :241 g_adv) -------------------------------
+ * y_last: the GRU stack's output at t = T-1, (n_half*B, H) rows `ld` floats apart; half 0 = real batch, half 1 = fake
+ * batch (one forward call of D each, i.e. one power iteration each when `training`; u, v are updated in place like the
+ * reference's buffers).  tg_head_fwd writes wbar (n_half,H) = w/sigma, uv (n_half,1+H), sigma (n_half), p (n_half*B)
+ * and the four LOCAL batch sums stats = {sum bce_0, sum bce_1, #(p_0 > .5), #(p_1 < .5)} (labels NULL = all ones).
+ * After the caller has summed `stats` over the ranks (data parallel), tg_head_seed turns them into scal = {loss_bce,
+ * acc, scale} for a global batch of Bg samples per half and writes the R1 seed d(sum p_real)/d y_last (may be NULL)
+ * and the fake half's input gradient; tg_head_bwd (after the tangent forward produced hd = d y_last(real)/d eps, NULL
+ * without R1) writes the real half's gradients, the head's weight / bias gradients and the logged loss value. */
+int tg_head_fwd(void* stream, const float* y_last, long long ld, int B, int H, int n_half, const float* w,
+                const float* bias, float* u, float* v, int training, const float* labels, float* wbar, float* uv,
+                float* sigma, float* p, float* stats);
+int tg_head_seed(void* stream, const float* p, const float* labels, const float* wbar, const float* stats, float* scal,
+                 float* seed, float* gyf, int B, int H, float Bg, float target, float band);
+int tg_head_bwd(void* stream, const float* y_last, long long ld, const float* hd, long long ld_hd, const float* p,
+                const float* labels, const float* w, const float* wbar, const float* uv, const float* sigma,
+                const float* scal, const float* r1, float* gyr, float* ghd, float* gw, float* gb, float* loss_val, int B,
+                int H, float Bg, float gamma);
+/* gen_step (tt:241, D frozen): gy (B,H) = gout * d mean_b BCE(p_b, 1) / d y_last */
+int tg_head_adv_bwd(void* stream, const float* p, const float* wbar, const float* gout, float* gy, int B, int H,
+                    float Bg);
+
 /* Best-checkpoint rule of train_timegan.py:410-413 ("if g_total < best_ckpt_loss: save_ckpt(best_path, ...)") without
  * a host round trip per step: when value[0] < best[0] (both device floats) the n source tensors (weights, Adam
  * moments) are copied into the snapshot tensors `dst`, then best[0] = value[0] and best_step[0] = step.  The host

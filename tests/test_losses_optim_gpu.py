@@ -100,6 +100,92 @@ def test_bce_matches_nn_bceloss():
     assert abs(losses.bce(ps.to(DEV), ys.to(DEV)).item() - torch.nn.BCELoss()(ps, ys).item()) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,gamma,band", [(5, 8, 1.0, 0.15), (256, 64, 1.0, 0.15), (37, 56, 2.5, 0.23), (12, 24, 0.0, 0.0)])
+def test_fused_head_kernels_match_spectral_norm_linear_bceloss_autograd(B, H, gamma, band):
+    """csrc/head.cu against the reference's own building blocks on the CPU: torch.nn.utils.spectral_norm(nn.Linear(H,1))
+    in train mode (two forward calls = two power iterations, tm:92-98), nn.BCELoss (tt:70,196), the accuracy / throttle
+    arithmetic of tt:205-215, and autograd for every gradient incl. the R1 'sdot' term."""
+    import timegan_b200 as tg
+    from timegan_b200 import head
+    torch.manual_seed(B + H)
+    D = tg.Discriminator(H, H, 1, 0.0).train()
+    fc_ref = torch.nn.utils.spectral_norm(torch.nn.Linear(H, 1))
+    fc_ref.load_state_dict(D.fc.state_dict())
+    fc_ref.train()
+    T = 3
+    y_all = torch.randn(2 * B, T, H)                                     # the head reads the last step through a view
+    yl_r = y_all[:B, -1].clone().requires_grad_(True)
+    yl_f = y_all[B:, -1].clone().requires_grad_(True)
+    hd = torch.randn(B, H, requires_grad=True)
+    labels = torch.cat([0.8 + 0.2 * torch.rand(B), 0.2 * torch.rand(B)])
+    target = 0.525
+    # ---- reference ----
+    d_real = torch.sigmoid(fc_ref(yl_r))
+    wbar_r = fc_ref.weight.clone()                                       # W / sigma of the first call (kept in graph)
+    d_fake = torch.sigmoid(fc_ref(yl_f))
+    bce = torch.nn.BCELoss()
+    loss = 0.5 * (bce(d_real, labels[:B].reshape(B, 1)) + bce(d_fake, labels[B:].reshape(B, 1)))
+    seed_ref = torch.autograd.grad(d_real.sum(), yl_r, retain_graph=True)[0]
+    acc = 0.5 * ((d_real > 0.5).float().mean().item() + (d_fake < 0.5).float().mean().item())
+    scale = max(0.2, 1.0 - max(0.0, acc - target) / band) if band > 0 else 1.0
+    r1 = torch.tensor(0.731)
+    sdot = (d_real * (1 - d_real) * torch.nn.functional.linear(hd, wbar_r)).sum()
+    obj = (loss + (gamma / B) * sdot) * scale
+    ref = torch.autograd.grad(obj, [yl_r, yl_f, hd, fc_ref.weight_orig, fc_ref.bias], allow_unused=True)
+    # ---- kernels ----
+    Dd = D.to(DEV)
+    ya = y_all.to(DEV)
+    last = ya[:, -1, :]
+    hs = head.forward(Dd, last, labels.to(DEV), 2)
+    assert relerr(hs.p[:B], d_real.reshape(-1)) < 1e-5 and relerr(hs.p[B:], d_fake.reshape(-1)) < 1e-5
+    assert torch.allclose(Dd.fc.weight_u.cpu(), fc_ref.weight_u, atol=1e-6)
+    assert torch.allclose(Dd.fc.weight_v.cpu(), fc_ref.weight_v, atol=1e-6)
+    scal, seed, gyf = head.seed(hs, hs.stats, float(B), target, band, need_seed=True)
+    assert abs(scal[0].item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item()))
+    assert abs(scal[1].item() - acc) < 1e-6 and abs(scal[2].item() - scale) < 1e-6
+    assert relerr(seed, seed_ref) < 1e-5
+    hdl = hd.detach().to(DEV)
+    gyr, ghd, gw, gb, lv = head.backward(Dd, hs, last, hdl if gamma > 0 else None, scal, r1.to(DEV) if gamma > 0 else None,
+                                         float(B), gamma)
+    assert relerr(gyf, ref[1]) < 1e-5
+    assert relerr(gyr, ref[0]) < 1e-5
+    if gamma > 0:
+        assert relerr(ghd, ref[2]) < 1e-5
+    assert relerr(gw, ref[3]) < 2e-5 and relerr(gb, ref[4]) < 2e-5
+    want = (loss.item() + (0.5 * gamma * r1.item() if gamma > 0 else 0.0)) * scale
+    assert abs(lv.item() - want) <= 1e-5 * max(1.0, abs(want))
+    # ---- gen_step's frozen head: g_adv = bce(D(h), ones), a third power iteration ----
+    yl_g = torch.randn(B, H, requires_grad=True)
+    adv_ref = bce(torch.sigmoid(fc_ref(yl_g)), torch.ones(B, 1))
+    (3.0 * adv_ref).backward()
+    yg = yl_g.detach().to(DEV).requires_grad_(True)
+    adv = head.adv_loss(Dd, yg)
+    (3.0 * adv).backward()
+    assert abs(adv.item() - adv_ref.item()) <= 1e-5 * max(1.0, abs(adv_ref.item()))
+    assert relerr(yg.grad, yl_g.grad) < 1e-5
+    assert torch.allclose(Dd.fc.weight_u.cpu(), fc_ref.weight_u, atol=1e-6)
+
+
+def test_fused_head_saturated_probabilities_follow_aten():
+    """BCELoss clamps its log terms at -100 and its backward divides by max(p(1-p), 1e-12): a saturated sigmoid must
+    give the same finite loss and zero-ish gradient, not inf / nan."""
+    import timegan_b200 as tg
+    from timegan_b200 import head
+    H, B = 8, 4
+    D = tg.Discriminator(H, H, 1, 0.0).train().to(DEV)
+    with torch.no_grad():
+        D.fc.bias.fill_(0.0)
+    last = torch.zeros(2 * B, H, device=DEV)
+    last[:B] = 400.0 * torch.sign(D.fc.weight_orig.detach())          # p -> 1 exactly
+    last[B:] = -400.0 * torch.sign(D.fc.weight_orig.detach())         # p -> 0 exactly
+    labels = torch.cat([torch.zeros(B), torch.ones(B)]).to(DEV)          # the worst case: log(0) on both halves
+    hs = head.forward(D, last, labels, 2)
+    scal, seed, gyf = head.seed(hs, hs.stats, float(B), 0.5, 0.1, need_seed=True)
+    assert abs(scal[0].item() - 100.0) < 1e-3 and torch.isfinite(seed).all() and torch.isfinite(gyf).all()
+    ref = torch.nn.BCELoss()(torch.tensor([[1.0], [0.0]]), torch.tensor([[0.0], [1.0]]))
+    assert abs(ref.item() - 100.0) < 1e-3
+
+
 @pytest.mark.parametrize("B,T,C,L", [(3, 40, 14, 8), (32, 768, 14, 64), (4, 100, 14, 200)])
 def test_cov_and_acf_terms(B, T, C, L):
     from timegan_b200 import losses
