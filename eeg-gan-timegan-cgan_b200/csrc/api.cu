@@ -137,14 +137,16 @@ int tg_use_cluster() {
   return x;
 }
 
-// two-columns-per-thread BPTT kernel for one-sequence-per-CTA launches at H <= 64 (gru_bwd.cu); TIMEGAN_B200_BWD_PAIR=0
-// / tg_set_option("bwd_pair", 0) switches back to the one-column kernel
+// two-columns-per-thread BPTT kernel for one-sequence-per-CTA launches at H <= 64 (gru_bwd.cu): OFF by default -- it
+// halves the shared-memory operand fetches (12 instead of 24 LDS.128 per step) but pays a second shuffle round on the
+// per-step dependency chain, and measured 283 vs 275 us at the c2 layer shape (profiles/r02_probe_bwd_pair.log).
+// TIMEGAN_B200_BWD_PAIR=1 / tg_set_option("bwd_pair", 1) selects it.
 static std::atomic<int> g_bwd_pair{-1};
 int tg_bwd_pair() {
   int x = g_bwd_pair.load(std::memory_order_relaxed);
   if (x < 0) {
     const char* e = getenv("TIMEGAN_B200_BWD_PAIR");
-    x = (e && atoi(e) == 0) ? 0 : 1;
+    x = (e && atoi(e) != 0) ? 1 : 0;
     g_bwd_pair.store(x);
   }
   return x;

@@ -100,6 +100,24 @@ __device__ __forceinline__ void reduce_scatter(float (&v)[N], int q) {
   }
 }
 
+// N lanes, M <= N partials per lane (M, N powers of two): afterwards v[0] of lane q is the total of index q % M (every
+// total is held by N/M lanes): log2(M) halving exchange rounds, then log2(N/M) butterfly adds
+template <int N, int M>
+__device__ __forceinline__ void reduce_partial(float (&v)[M], int q) {
+#pragma unroll
+  for (int s = M / 2; s >= 1; s >>= 1) {
+    const bool up = (q & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+#pragma unroll
+  for (int s = M; s < N; s <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], s);
+}
+
 // =====================================================================================================================
 // forward
 // =====================================================================================================================
@@ -112,18 +130,19 @@ struct ClFwdParams {
   int B, T, save;
 };
 
-template <int H, int CS, int NGRP>
+// SG = sequences per group (G or G/2), NGRP groups per cluster, each with its own pair of barriers
+template <int H, int CS, int NGRP, int SG>
 struct ClFwdSmem {
-  static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
+  static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = SG * NGRP, HR = H + CL_HPAD;
   static constexpr int HBUF = 2 * BT * HR;             // floats
   static constexpr int RING = CL_PF * BT * 3 * HU;     // floats
   static constexpr int STG = 2 * BT * 5 * HU;          // floats
   static constexpr size_t bytes = (size_t)(HBUF + RING + STG) * 4 + 128;
 };
 
-template <int H, int CS, int NGRP>
+template <int H, int CS, int NGRP, int SG>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams p) {
-  using S = ClFwdSmem<H, CS, NGRP>;
+  using S = ClFwdSmem<H, CS, NGRP, SG>;
   constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR, KS = H / G;
   static_assert(KS == 32, "96 weight registers per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -139,7 +158,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   const bool save = p.save != 0;
 
   for (int i = tid; i < S::HBUF + S::RING; i += CL_THREADS) hbuf[i] = 0.f;     // h_{-1} = 0; ring rows of absent sequences
-  constexpr uint32_t TXB = (uint32_t)(H * G * 4);                   // bytes one group receives per step
+  static_assert(SG == G || SG * 2 == G, "a group is G or G/2 sequences");
+  constexpr uint32_t TXB = (uint32_t)(H * SG * 4);                  // bytes one group receives per step
   if (tid == 0) {
     for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&bars[i], 1);
     mbar_fence_init();
@@ -214,11 +234,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   uint32_t r_h[ND], r_bar[ND];
   bool r_ok[ND];
 #pragma unroll
+  const int ob = ql % SG;                           // the sequence (within a group) this lane finishes
+  const bool primary = ql < SG;                     // SG < G: lanes ql and ql + SG hold the same totals; one of them stores
   for (int d = 0; d < ND; ++d) {
     const int c = (jl & 3) + 4 * d;
-    r_ok[d] = c < CS;
-    r_h[d] = mapa_shared(smem_u32(hbuf + ql * HR + (j & ~3)), (uint32_t)(r_ok[d] ? c : 0));
-    r_bar[d] = mapa_shared(smem_u32(bars), (uint32_t)(r_ok[d] ? c : 0));
+    r_ok[d] = primary && c < CS;
+    r_h[d] = mapa_shared(smem_u32(hbuf + ob * HR + (j & ~3)), (uint32_t)(c < CS ? c : 0));
+    r_bar[d] = mapa_shared(smem_u32(bars), (uint32_t)(c < CS ? c : 0));
   }
   float hprev[NGRP];
 #pragma unroll
@@ -232,6 +254,45 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     prefetch(t + CL_PF - 1);
     const int par = t & 1, ppar = par ^ 1;
     float* sgw = stg + par * (BT * 5 * HU);
+    const float* ringt = ring + (t % CL_PF) * (BT * 3 * HU);
+    // everything after a group's mat-vec: combine the lane partials, gates, state update, all-gather, staging
+    auto post = [&](const int grp, float2 (&acc)[SG][3]) __attribute__((always_inline)) {
+      const float* gr_ = ringt + ((grp * SG + ob) * 3) * HU + jl;
+      const float gr = gr_[0], gz = gr_[HU], gn = gr_[2 * HU];
+      float own[3];
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        float v[SG];
+#pragma unroll
+        for (int b = 0; b < SG; ++b) v[b] = acc[b][g].x + acc[b][g].y;
+        reduce_partial<G, SG>(v, ql);
+        own[g] = v[0];
+      }
+      const float r = sigmoid_mufu(gr + own[0]);
+      const float z = sigmoid_mufu(gz + own[1]);
+      const float qv = own[2] + bh[2];
+      const float n = tanh_mufu(fmaf(r, qv, gn));
+      const float h = fmaf(z, hprev[grp] - n, n);
+      hprev[grp] = h;
+      // all-gather: h_t[b][j] into every CTA's state vector (parity t&1), signalling that CTA's barrier
+      if (t + 1 < T) {
+        const uint32_t off = (uint32_t)((par * BT + grp * SG) * HR) * 4u;
+        const float h0 = __shfl_sync(0xffffffffu, h, src0), h1 = __shfl_sync(0xffffffffu, h, src0 + G),
+                    h2 = __shfl_sync(0xffffffffu, h, src0 + 2 * G), h3 = __shfl_sync(0xffffffffu, h, src0 + 3 * G);
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+          if (r_ok[d]) st_async_v4(r_h[d] + off, h0, h1, h2, h3, r_bar[d] + (uint32_t)(grp * 2 + par) * 8u);
+      }
+      if (primary) {
+        float* so = sgw + ((grp * SG + ob) * 5) * HU + jl;
+        so[0] = r; so[HU] = z; so[2 * HU] = n; so[3 * HU] = qv; so[4 * HU] = h;
+      }
+    };
+    // With several groups, group g's post-processing (a chain of dependent shuffles and MUFU ops) sits in the same basic
+    // block as group g+1's mat-vec so that the scheduler may interleave them.  Half-size groups (SG = G/2, twice as many
+    // of them) were tried to hide the chain at B <= 296 too: 2267 vs 2006 clk/step at H = 128 -- the duplicated gate work
+    // and the second barrier wait cost more than the overlap gains -- so the launcher uses SG = G.
+    float2 accs[2][SG][3];
 #pragma unroll
     for (int grp = 0; grp < NGRP; ++grp) {
       // ---- wait for h_{t-1} of this group (all CTAs' slices) ----
@@ -239,20 +300,18 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((t - 1) >> 1) & 1));
         if (tid == 0 && t + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);   // re-arm for step t+1's values
       }
-      const float* gr_ = ring + (((t % CL_PF) * BT + grp * G + ql) * 3) * HU + jl;
-      const float gr = gr_[0], gz = gr_[HU], gn = gr_[2 * HU];
-      float2 acc[G][3];
+      float2 (&acc)[SG][3] = accs[grp & 1];
 #pragma unroll
-      for (int b = 0; b < G; ++b) {
+      for (int b = 0; b < SG; ++b) {
         acc[b][0] = make_float2((b == ql) ? bh[0] : 0.f, 0.f);
         acc[b][1] = make_float2((b == ql) ? bh[1] : 0.f, 0.f);
         acc[b][2] = make_float2(0.f, 0.f);
       }
-      const uint32_t hc = hbuf_a + (uint32_t)((ppar * BT + grp * G) * HR) * 4u + 16u * (uint32_t)ql;
+      const uint32_t hc = hbuf_a + (uint32_t)((ppar * BT + grp * SG) * HR) * 4u + 16u * (uint32_t)ql;
 #pragma unroll
       for (int i = 0; i < KS / 4; ++i) {
 #pragma unroll
-        for (int b = 0; b < G; ++b) {
+        for (int b = 0; b < SG; ++b) {
           const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u);
           const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
 #pragma unroll
@@ -262,33 +321,9 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
           }
         }
       }
-      float own[3];
-#pragma unroll
-      for (int g = 0; g < 3; ++g) {
-        float v[G];
-#pragma unroll
-        for (int b = 0; b < G; ++b) v[b] = acc[b][g].x + acc[b][g].y;
-        reduce_scatter<G>(v, ql);
-        own[g] = v[0];
-      }
-      const float r = sigmoid_mufu(gr + own[0]);
-      const float z = sigmoid_mufu(gz + own[1]);
-      const float qv = own[2] + bh[2];
-      const float n = tanh_mufu(fmaf(r, qv, gn));
-      const float h = fmaf(z, hprev[grp] - n, n);
-      hprev[grp] = h;
-      // ---- all-gather: h_t[b][j] into every CTA's state vector (parity t&1), signalling that CTA's barrier ----
-      if (t + 1 < T) {
-        const uint32_t off = (uint32_t)((par * BT + grp * G) * HR) * 4u;
-        const float h0 = __shfl_sync(0xffffffffu, h, src0), h1 = __shfl_sync(0xffffffffu, h, src0 + G),
-                    h2 = __shfl_sync(0xffffffffu, h, src0 + 2 * G), h3 = __shfl_sync(0xffffffffu, h, src0 + 3 * G);
-#pragma unroll
-        for (int d = 0; d < ND; ++d)
-          if (r_ok[d]) st_async_v4(r_h[d] + off, h0, h1, h2, h3, r_bar[d] + (uint32_t)(grp * 2 + par) * 8u);
-      }
-      float* so = sgw + ((grp * G + ql) * 5) * HU + jl;
-      so[0] = r; so[HU] = z; so[2 * HU] = n; so[3 * HU] = qv; so[4 * HU] = h;
+      if (grp > 0) post(grp - 1, accs[(grp - 1) & 1]);
     }
+    post(NGRP - 1, accs[(NGRP - 1) & 1]);
   }
   __syncthreads();
   store(T - 1);
@@ -521,10 +556,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   cluster_sync_all();
 }
 
-template <int H, int CS, int NGRP>
+template <int H, int CS, int NGRP, int SG>
 int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
-  using S = ClFwdSmem<H, CS, NGRP>;
-  auto kern = gru_cl_fwd_kernel<H, CS, NGRP>;
+  using S = ClFwdSmem<H, CS, NGRP, SG>;
+  auto kern = gru_cl_fwd_kernel<H, CS, NGRP, SG>;
   TG_OPT_IN_SMEM(kern, "gru_cl_fwd");
   const int clusters = (p.B + S::BT - 1) / S::BT;
   kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
@@ -567,11 +602,11 @@ int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh
   const int sms = tg_num_sms();
   if (H == 128) {
     const int clusters1 = (B + 3) / 4;
-    return (clusters1 * 2 <= sms) ? launch_cl_fwd<128, 2, 1>(st, p) : launch_cl_fwd<128, 2, 2>(st, p);
+    return (clusters1 * 2 <= sms) ? launch_cl_fwd<128, 2, 1, 4>(st, p) : launch_cl_fwd<128, 2, 2, 4>(st, p);
   }
   if (H == 256) {
     const int clusters1 = (B + 7) / 8;
-    return (clusters1 * 8 <= sms) ? launch_cl_fwd<256, 8, 1>(st, p) : launch_cl_fwd<256, 8, 2>(st, p);
+    return (clusters1 * 8 <= sms) ? launch_cl_fwd<256, 8, 1, 8>(st, p) : launch_cl_fwd<256, 8, 2, 8>(st, p);
   }
   tg_set_error("gru_cl_fwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;

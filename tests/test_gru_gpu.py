@@ -126,6 +126,32 @@ def test_cluster_kernels_forced(B, T, H, dy_last):
         assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
 
 
+@pytest.mark.parametrize("B,T,I,H,L,dy_last", [(9, 200, 14, 64, 3, False), (6, 64, 24, 24, 3, True), (4, 100, 28, 56, 1, False)])
+def test_two_columns_per_thread_bptt_variant(B, T, I, H, L, dy_last):
+    """gru_bwd_pair_kernel (one sequence per CTA, a lane group owns two adjacent output columns): same gradients as
+    the default kernel's reference.  Off by default (measured slower); kept selectable."""
+    from timegan_b200._lib import lib
+    ops = _ops()
+    m = make_gru(I, H, L, seed=7 * B + H)
+    g = torch.Generator().manual_seed(B + 1)
+    x = torch.rand(B, T, I, generator=g, requires_grad=True)
+    y_ref, _ = m(x)
+    dy = torch.randn(B, H, generator=g) if dy_last else torch.randn(B, T, H, generator=g)
+    obj = (y_ref[:, -1] * dy).sum() if dy_last else (y_ref * dy).sum()
+    ref = torch.autograd.grad(obj, [x] + list(m.parameters()))
+    dev = torch.device("cuda:0")
+    w = flat_weights(m, dev)
+    assert lib.tg_set_option(b"bwd_pair", 1) == 0
+    try:
+        _, saves = ops.stack_forward(x.detach().to(dev), w, save=True)
+        dx, grads = ops.stack_backward(dy.to(dev), saves, w, need_dx=True, need_dw=True, dy_last=dy_last)
+    finally:
+        lib.tg_set_option(b"bwd_pair", 0)
+    assert relerr(dx, ref[0]) < TOL
+    for k, gk in enumerate(grads):
+        assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
+
+
 def test_last_step_only_gradient():
     """Discriminator pattern (timegan_model.py:97): only y[:, -1] feeds the loss."""
     ops = _ops()

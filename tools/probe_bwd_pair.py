@@ -22,4 +22,4 @@ for H, B in [(64, 256), (64, 148), (24, 256), (56, 64)]:
         p = _lib.prof_read()
         f, b = p['gru_fwd']['ms'] / p['gru_fwd']['calls'] * 1e3, p['gru_bwd']['ms'] / p['gru_bwd']['calls'] * 1e3
         print(f"H={H} B={B} pair={pair}: fwd {f:7.1f} us | bwd {b:7.1f} us  {b * 1965 / T:5.0f} clk/step", flush=True)
-lib.tg_set_option(b"bwd_pair", 1)
+lib.tg_set_option(b"bwd_pair", 0)
