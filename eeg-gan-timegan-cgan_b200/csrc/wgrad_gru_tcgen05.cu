@@ -12,6 +12,9 @@
 // deterministic partial reduction, fix-up warps (h_{-1} rows, bias column sums, 3xTF32 split).  The lo parts of the
 // 3xTF32 split live in THREE shared buffers (they are only needed while a stage's MMAs run), which leaves room for
 // a 6-deep ring of raw stages -- the kernel is bound by bytes in flight, not by math.
+// TMEM holds 512 accumulator columns: MT M-tiles x (I+H padded) columns.  When the whole [dGI | dq] operand does not fit
+// (H = 128: 4 M-tiles x 256 columns), the layer is done in several launches, each owning a range of M-tiles (i.e. of
+// dGI / dq columns) and streaming only those columns plus x and y; all launches write disjoint parts of one workspace.
 #include "tc_common.cuh"
 #include "kernels.h"
 
@@ -28,9 +31,10 @@ struct WlParams {
   float* ws;        // [splits][3H*I + 3H*H + GCH*32] : dW_ih partial, dW_hh partial, column-sum partial
   int M, I, H, T;
   int R, nstage, rows_per_cta;
-  int g1ch, g2ch;   // 32-col chunks of dGI / dq
+  int g1ch, g2ch;   // 32-col chunks of dGI / dq (whole layer)
   int a1ch, a2ch;   // 32-col chunks of x (0 when x is absent) / y
   int MT, tmem_cols;
+  int mt0;          // first M-tile (128 rows of [dGI | dq]^T) of this launch; it covers MT tiles
 };
 
 template <int PASSES>
@@ -40,7 +44,10 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.R, NS = p.nstage;
-  const int GCH = p.g1ch + p.g2ch, ACH = p.a1ch + p.a2ch;
+  const int GTOT = p.g1ch + p.g2ch;                       // chunks of the whole [dGI | dq] operand
+  const int cbase = p.mt0 * 4;                            // first chunk of this launch
+  const int GCH = min(GTOT, cbase + p.MT * 4) - cbase;    // chunks of this launch
+  const int ACH = p.a1ch + p.a2ch;
   const int chunk_bytes = R * 128;
   const int stage_bytes = (GCH + ACH) * chunk_bytes;
   unsigned char* lo_base = smem + (size_t)NS * stage_bytes;                    // [2][stage_bytes] (3-pass only)
@@ -84,8 +91,11 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
         unsigned char* dst = smem + (size_t)s * stage_bytes;
         const int r0 = (int)(row_begin + (long long)it * R);
         int c = 0;
-        for (int k = 0; k < p.g1ch; ++k, ++c) tma_load_2d(dst + c * chunk_bytes, &tmG1, &full[s], k * 32, r0);
-        for (int k = 0; k < p.g2ch; ++k, ++c) tma_load_2d(dst + c * chunk_bytes, &tmG2, &full[s], k * 32, r0);
+        for (; c < GCH; ++c) {
+          const int cg = cbase + c;
+          if (cg < p.g1ch) tma_load_2d(dst + c * chunk_bytes, &tmG1, &full[s], cg * 32, r0);
+          else tma_load_2d(dst + c * chunk_bytes, &tmG2, &full[s], (cg - p.g1ch) * 32, r0);
+        }
         for (int k = 0; k < p.a1ch; ++k, ++c) tma_load_2d(dst + c * chunk_bytes, &tmA1, &full[s], k * 32, r0);
         for (int k = 0; k < p.a2ch; ++k, ++c) tma_load_2d(dst + c * chunk_bytes, &tmA2, &full[s], k * 32, r0 - 1);
       }
@@ -132,11 +142,11 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
     mbar_wait_bounded(acc_full, 0);
     tc_fence_after();
     const int I = p.I, H = p.H;
-    float* w_ih = p.ws + (size_t)blockIdx.x * ((size_t)3 * H * I + (size_t)3 * H * H + GCH * 32);
+    float* w_ih = p.ws + (size_t)blockIdx.x * ((size_t)3 * H * I + (size_t)3 * H * H + GTOT * 32);
     float* w_hh = w_ih + (size_t)3 * H * I;
     const int ycol0 = p.a1ch * 32;     // first accumulator column of the y block
     for (int mt = 0; mt < p.MT; ++mt) {
-      const int n = mt * 128 + quarter * 32 + lane;     // logical row of [dGI | pad | dq]
+      const int n = (p.mt0 + mt) * 128 + quarter * 32 + lane;     // logical row of [dGI | pad | dq]
       const int nq = n - p.g1ch * 32;                    // row inside dq (>= 0 for the dq block)
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(mt * NB);
       for (int c0 = 0; c0 < NB; c0 += 16) {
@@ -233,8 +243,8 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
       if (c < GCH) *reinterpret_cast<float4*>(db_red + (size_t)rsub * (GCH * 32) + c * 32 + cu * 4) = colsum[ci];
     }
     asm volatile("bar.sync 1, %0;" ::"n"(WL_FIX) : "memory");
-    float* cs = p.ws + (size_t)blockIdx.x * ((size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H + GCH * 32) +
-                (size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H;
+    float* cs = p.ws + (size_t)blockIdx.x * ((size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H + GTOT * 32) +
+                (size_t)3 * p.H * p.I + (size_t)3 * p.H * p.H + cbase * 32;
     for (int n = t; n < GCH * 32; n += WL_FIX) {
       float sum = 0.f;
 #pragma unroll
@@ -317,22 +327,25 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
   const int g1ch = (3 * H + 31) / 32, g2ch = (H + 31) / 32, a1ch = x ? (I + 31) / 32 : 0, a2ch = (H + 31) / 32;
   const int GCH = g1ch + g2ch, ACH = a1ch + a2ch, MT = (GCH + 3) / 4;
   const bool ok = (H % 4 == 0) && (!x || (ldx % 4 == 0 && tg_aligned16(x))) && tg_aligned16(dgi) && tg_aligned16(dq) &&
-                  tg_aligned16(y) && GCH <= WL_MAXCH && ACH * 32 <= 256 && MT * ACH * 32 <= 512 && M >= 256 &&
-                  Mll < (1ll << 31);
+                  tg_aligned16(y) && GCH <= WL_MAXCH && ACH * 32 <= 256 && M >= 256 && Mll < (1ll << 31);
   if (!ok) { tg_set_error("wgrad_gru: shape/alignment not supported by the fused tensor-core tile"); return TG_ERR_UNSUPPORTED; }
   const int Iw = x ? I : 0;
   TG_REQUIRE(ws_bytes >= tg_wgrad_gru_ws_bytes(M, Iw, H), TG_ERR_ARG, "wgrad_gru: workspace too small");
+  // M-tiles per launch: what 512 TMEM columns hold next to each other (all of them up to H = 96; two at H = 128)
+  int MTL = 512 / (ACH * 32);
+  if (MTL > MT) MTL = MT;
+  const int gch_l = (MTL * 4 < GCH) ? MTL * 4 : GCH;      // widest chunk range of a launch
   int R = 32, nstage = 0;
   for (; R >= 8; R >>= 1) {
-    const int stage_bytes = (GCH + ACH) * R * 128;
+    const int stage_bytes = (gch_l + ACH) * R * 128;
     nstage = (tg_gemm_smem_budget() - WL_TAIL - 4 * R * 128) / stage_bytes - (passes == 3 ? WL_NLO : 0);
     if (nstage >= 4) break;
   }
   if (R < 8 || nstage < 3) { tg_set_error("wgrad_gru: tile does not fit shared memory"); return TG_ERR_UNSUPPORTED; }
   if (nstage > 8) nstage = 8;
-  const int stage_bytes = (GCH + ACH) * R * 128;
+  const int stage_bytes = (gch_l + ACH) * R * 128;
   size_t smem = (size_t)(nstage + (passes == 3 ? WL_NLO : 0)) * stage_bytes + WL_TAIL + 4 * (size_t)R * 128;
-  if (smem < (size_t)16 * GCH * 32 * 4 + WL_TAIL) smem = (size_t)16 * GCH * 32 * 4 + WL_TAIL;
+  if (smem < (size_t)16 * gch_l * 32 * 4 + WL_TAIL) smem = (size_t)16 * gch_l * 32 * 4 + WL_TAIL;
 
   alignas(64) CUtensorMap tmG1, tmG2, tmA1, tmA2;
   if (tg_make_map_2d(&tmG1, dgi, M, 3 * H, 3 * H, 32, R, true) != TG_OK) return TG_ERR_UNSUPPORTED;
@@ -346,13 +359,18 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
   const int splits = wl_splits(M);
   int rows_per = (M + splits - 1) / splits;
   rows_per = (rows_per + R - 1) / R * R;
-  WlParams p{ws, M, Iw, H, T, R, nstage, rows_per, g1ch, g2ch, a1ch, a2ch, MT, pow2c(MT * ACH * 32)};
-  if (passes == 3) {
-    TG_OPT_IN_SMEM(tc_wgrad_layer_kernel<3>, "wgrad_gru");
-    tc_wgrad_layer_kernel<3><<<splits, WL_THREADS, smem, st>>>(tmG1, tmG2, tmA1, tmA2, p);
-  } else {
-    TG_OPT_IN_SMEM(tc_wgrad_layer_kernel<1>, "wgrad_gru");
-    tc_wgrad_layer_kernel<1><<<splits, WL_THREADS, smem, st>>>(tmG1, tmG2, tmA1, tmA2, p);
+  for (int mt0 = 0; mt0 < MT; mt0 += MTL) {
+    const int mtl = (MT - mt0 < MTL) ? MT - mt0 : MTL;
+    WlParams p{ws, M, Iw, H, T, R, nstage, rows_per, g1ch, g2ch, a1ch, a2ch, mtl, pow2c(mtl * ACH * 32), mt0};
+    if (passes == 3) {
+      TG_OPT_IN_SMEM(tc_wgrad_layer_kernel<3>, "wgrad_gru");
+      tc_wgrad_layer_kernel<3><<<splits, WL_THREADS, smem, st>>>(tmG1, tmG2, tmA1, tmA2, p);
+    } else {
+      TG_OPT_IN_SMEM(tc_wgrad_layer_kernel<1>, "wgrad_gru");
+      tc_wgrad_layer_kernel<1><<<splits, WL_THREADS, smem, st>>>(tmG1, tmG2, tmA1, tmA2, p);
+    }
+    int rcl = tg_check_launch("wgrad_gru");
+    if (rcl) return rcl;
   }
   int rc = tg_check_launch("wgrad_gru");
   if (rc) return rc;
