@@ -84,10 +84,14 @@ def parse():
     return ap.parse_args()
 
 
+PROJ_LABEL = {"fp32": "fp32 (3xTF32) projections",
+              "bf16": "reduced-precision projections (one TF32 pass over fp32 operands; BASELINE's 'bf16 input projections' slot)"}
+
+
 def workload_name(a):
     cfg = "c2" if (a.hidden, a.layers, a.batch) == (64, 3, 256) else "custom"
     return (f"{cfg}: TimeGAN joint step (disc_step+gen_step) z=h={a.hidden} L={a.layers} B={a.batch}/GPU "
-            f"T={T_LEN} C={X_DIM} {a.proj} projections")
+            f"T={T_LEN} C={X_DIM} {PROJ_LABEL[a.proj]}")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -299,7 +303,7 @@ def secondary_config(a, dev, world, rank, hidden, proj, label, steps=6, warmup=3
         del model, optD, optG, xs
         torch.cuda.empty_cache()
         return {"workload": f"{label}: TimeGAN joint step z=h={hidden} L={a.layers} B={a.batch}/GPU T={T_LEN} C={X_DIM} "
-                            f"{proj} projections", "global_batch": a.batch * world, "value": round(a.batch * world * steps / (ms * 1e-3), 2),
+                            f"{PROJ_LABEL[proj]}", "global_batch": a.batch * world, "value": round(a.batch * world * steps / (ms * 1e-3), 2),
                 "unit": "seq/s", "ms_per_step": round(ms / steps, 3), "steps": steps, "warmup": warmup,
                 "issue": "cuda-graph replay" if use_graph else "eager", "finite": ok}
     finally:
@@ -488,7 +492,7 @@ def run_ours(a):
     line = {
         "metric": METRIC, "value": round(seqs / (ms * 1e-3), 2), "unit": "seq/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if a.proj == "fp32" else "fp32 (bf16 projections)",
+        "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if a.proj == "fp32" else "fp32 (tf32 projections)",
         "data": "synthetic",
         "config": bench_config(a, world),
         "e2e": {"value": round(seqs / (ms_e2e * 1e-3), 2), "unit": "seq/s",

@@ -556,6 +556,270 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   cluster_sync_all();
 }
 
+// =====================================================================================================================
+// reverse over (primal + tangent) forward -- the R1 double backward (train_timegan.py:198-202)
+// =====================================================================================================================
+// Same skeleton as the BPTT kernel, with TWO carried adjoints (hb of y, hdb of ydot) that share the register-resident
+// W_hh^T slices: six vectors are all-gathered per step (primal dGH: arb, azb, qb; tangent dGH: arb_d, azb_d, qdb) and
+// two mat-vecs are accumulated from them.  Every output of a step is linear in (hb, hdb) with coefficients that only
+// depend on saved activations (derivation: oracle/gru_math.py gru_layer_jvp_bwd; the one-SM kernel gru_jvp_bwd_kernel of
+// gru_jvp.cu uses the same coefficient pairs), so they are formed before the mbarrier wait.
+struct ClJbParams {
+  const float* hbar;   // (B,T,H) or (B,H) if last_only
+  const float* hdbar;
+  const float* rzn;    // (B,T,3H)
+  const float* q;      // (B,T,H)
+  const float* ta;     // (B,T,3H) tangent pre-activations
+  const float* qdot;   // (B,T,H)
+  const float* y;      // (B,T,H)
+  const float* ydot;   // (B,T,H)
+  const float* whh;
+  float* gib;          // (B,T,3H)
+  float* qb;           // (B,T,H)
+  float* gidb;         // (B,T,3H)
+  float* qdb;          // (B,T,H)
+  int B, T, last_only;
+};
+
+template <int H, int CS, int NGRP>
+struct ClJbSmem {
+  static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
+  static constexpr int DBUF = 2 * BT * 6 * HR;
+  static constexpr int RING = CL_PF * BT * 12 * HU;    // r,z,n,q, ar,az,an,qd, h_{t-1}, hd_{t-1}, hbar, hdbar
+  static constexpr int STG = 2 * BT * 8 * HU;          // arb,azb,anb,qb, arb_d,azb_d,anb_d,qdb
+  static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
+};
+
+template <int H, int CS, int NGRP>
+__global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_jvp_bwd_kernel(ClJbParams p) {
+  using S = ClJbSmem<H, CS, NGRP>;
+  constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR;
+  constexpr int L2 = 2 * G, J = H / L2;
+  static_assert(J == 16, "96 weight registers per thread");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* dbuf = reinterpret_cast<float*>(smem_raw + 128);            // [2][BT][6][HR]
+  float* ring = dbuf + S::DBUF;                                      // [PF][BT][12][HU]
+  float* stg = ring + S::RING;                                       // [2][BT][8][HU]
+  const int tid = threadIdx.x, kp = tid / L2, ql = tid % L2;
+  const uint32_t rank = cluster_ctarank();
+  const int T = p.T;
+  const int b0 = (blockIdx.x / CS) * BT;
+  const int ob = ql % G, oo = ql / G;
+  const int kl = 2 * kp + oo;
+  const int k = (int)rank * HU + kl;
+
+  for (int i = tid; i < S::DBUF + S::RING; i += CL_THREADS) dbuf[i] = 0.f;
+  constexpr uint32_t TXB = (uint32_t)(6 * H * G * 4);
+  if (tid == 0) {
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&bars[i], 1);
+    mbar_fence_init();
+    for (int i = 0; i < 2 * NGRP; ++i) mbar_expect_tx(&bars[i], TXB);
+  }
+  __syncthreads();
+
+  // ---- this thread's share of the step's HBM traffic ----
+  constexpr int Q = HU / 4;
+  constexpr int NLI = BT * 12 * Q, NSI = BT * 8 * Q;
+  constexpr int NLD = (NLI + CL_THREADS - 1) / CL_THREADS, NSD = (NSI + CL_THREADS - 1) / CL_THREADS;
+  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * 12 * HU) * 4u, STG_BYTES = (uint32_t)(BT * 8 * HU) * 4u;
+  const float* lp[NLD]; uint32_t ls[NLD]; bool lv[NLD]; int lst[NLD]; bool lshift[NLD];
+#pragma unroll
+  for (int m = 0; m < NLD; ++m) {
+    const int n = tid + CL_THREADS * m, j4 = n % Q, wch = (n / Q) % 12, b = n / (12 * Q);
+    lv[m] = (n < NLI) && (b0 + b < p.B) && !(wch >= 10 && p.last_only);
+    const size_t seq = (size_t)(b0 + (lv[m] ? b : 0)) * T;
+    const int col = (int)rank * HU + j4 * 4;
+    lshift[m] = (wch == 8 || wch == 9);                    // h_{t-1} / hd_{t-1}: row t-1, nothing at t = 0
+    const float* base = p.q + seq * H;
+    if (wch < 3) base = p.rzn + seq * (3 * H) + wch * H;
+    else if (wch == 3) base = p.q + seq * H;
+    else if (wch < 7) base = p.ta + seq * (3 * H) + (wch - 4) * H;
+    else if (wch == 7) base = p.qdot + seq * H;
+    else if (wch == 8) base = p.y + seq * H - H;
+    else if (wch == 9) base = p.ydot + seq * H - H;
+    else if (!p.last_only) base = (wch == 10 ? p.hbar : p.hdbar) + seq * H;
+    lp[m] = base + col;
+    lst[m] = (wch < 3 || (wch >= 4 && wch < 7)) ? 3 * H : H;
+    ls[m] = smem_u32(ring) + (uint32_t)((b * 12 + wch) * HU + j4 * 4) * 4u;
+  }
+  float* sp[NSD]; uint32_t ss[NSD]; bool sv[NSD]; int sst[NSD];
+#pragma unroll
+  for (int m = 0; m < NSD; ++m) {
+    const int n = tid + CL_THREADS * m, j4 = n % Q, wch = (n / Q) % 8, b = n / (8 * Q);
+    sv[m] = (n < NSI) && (b0 + b < p.B);
+    const size_t seq = (size_t)(b0 + (sv[m] ? b : 0)) * T;
+    float* base = (wch < 3) ? p.gib + seq * (3 * H) + wch * H
+                  : (wch == 3 ? p.qb + seq * H : (wch < 7 ? p.gidb + seq * (3 * H) + (wch - 4) * H : p.qdb + seq * H));
+    sp[m] = base + (int)rank * HU + j4 * 4;
+    sst[m] = (wch < 3 || (wch >= 4 && wch < 7)) ? 3 * H : H;
+    ss[m] = smem_u32(stg) + (uint32_t)((b * 8 + wch) * HU + j4 * 4) * 4u;
+  }
+  auto prefetch = [&](int t) {
+    if (t >= 0) {
+      const uint32_t so = (uint32_t)(t % CL_PF) * SLOT_BYTES;
+#pragma unroll
+      for (int m = 0; m < NLD; ++m)
+        if (lv[m] && !(lshift[m] && t == 0)) cp_async16(ls[m] + so, lp[m] + (size_t)t * lst[m]);
+    }
+    cp_async_commit();
+  };
+  auto store = [&](int t, int s) {
+    const uint32_t so = (uint32_t)(s & 1) * STG_BYTES;
+#pragma unroll
+    for (int m = 0; m < NSD; ++m)
+      if (sv[m]) *reinterpret_cast<float4*>(sp[m] + (size_t)t * sst[m]) = lds_v4(ss[m] + so);
+  };
+  for (int s = 0; s < CL_PF - 1; ++s) prefetch(T - 1 - s);
+
+  float2 wt[2][3][J / 2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+#pragma unroll
+      for (int i = 0; i < J / 4; ++i) {
+        const int jj = (i * L2 + ql) * 4;
+        const int kk = (int)rank * HU + 2 * kp + o;
+        const float a0 = p.whh[(size_t)(g * H + jj + 0) * H + kk], a1 = p.whh[(size_t)(g * H + jj + 1) * H + kk];
+        const float a2 = p.whh[(size_t)(g * H + jj + 2) * H + kk], a3 = p.whh[(size_t)(g * H + jj + 3) * H + kk];
+        wt[o][g][2 * i] = make_float2(a0, a1);
+        wt[o][g][2 * i + 1] = make_float2(a2, a3);
+      }
+  cluster_sync_all();
+
+  const int lane = tid & 31;
+  const int wbase = lane - (kp % (32 / L2)) * L2 - oo * G;
+  const int kr = (kl & ~3) - 2 * (kp - kp % (32 / L2));
+  int srcl[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) srcl[i] = wbase + ((kr + i) >> 1) * L2 + ((kr + i) & 1) * G;
+  constexpr int ND = (CS + 3) / 4;
+  uint32_t r_d[ND], r_bar[ND];
+  bool r_ok[ND];
+#pragma unroll
+  for (int d = 0; d < ND; ++d) {
+    const int c = (kl & 3) + 4 * d;
+    r_ok[d] = c < CS;
+    r_d[d] = mapa_shared(smem_u32(dbuf + (ob * 6) * HR + (k & ~3)), (uint32_t)(r_ok[d] ? c : 0));
+    r_bar[d] = mapa_shared(smem_u32(bars), (uint32_t)(r_ok[d] ? c : 0));
+  }
+  float ch[NGRP], chd[NGRP];
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) {
+    const bool on = p.last_only && (b0 + g * G + ob) < p.B;
+    ch[g] = on ? p.hbar[(size_t)(b0 + g * G + ob) * H + k] : 0.f;
+    chd[g] = on ? p.hdbar[(size_t)(b0 + g * G + ob) * H + k] : 0.f;
+  }
+  const uint32_t dbuf_a = smem_u32(dbuf);
+
+  for (int s = 0; s < T; ++s) {
+    const int t = T - 1 - s;
+    cp_async_wait<CL_PF - 2>();
+    __syncthreads();
+    if (s > 0) store(t + 1, s - 1);
+    prefetch(t - (CL_PF - 1));
+    const int par = s & 1, ppar = par ^ 1;
+    float* sgw = stg + par * (BT * 8 * HU);
+#pragma unroll
+    for (int grp = 0; grp < NGRP; ++grp) {
+      // ---- coefficient pairs of (b, t, k): out = alpha hb + beta hdb ----
+      const float* rg = ring + (((t % CL_PF) * BT + grp * G + ob) * 12) * HU + kl;
+      const float rt = rg[0], zt = rg[HU], nt = rg[2 * HU], qt = rg[3 * HU];
+      const float art = rg[4 * HU], azt = rg[5 * HU], ant = rg[6 * HU], qdt = rg[7 * HU];
+      const float hp = (t == 0) ? 0.f : rg[8 * HU], hdp = (t == 0) ? 0.f : rg[9 * HU];
+      const float fhb = p.last_only ? 0.f : rg[10 * HU], fhdb = p.last_only ? 0.f : rg[11 * HU];
+      const float sr = rt * (1.f - rt), omz = 1.f - zt, sz = zt * omz, sn = fmaf(-nt, nt, 1.f);
+      const float rdot = sr * art, zdot = sz * azt, ndot = sn * ant, hmn = hp - nt;
+      const float K1 = sn * omz;
+      const float K2 = sn * (-zdot - 2.f * nt * ant * omz);
+      const float rdbB = qt * K1;
+      const float ardB = sr * rdbB;
+      const float qA = rt * K1, qB = fmaf(rdot, K1, rt * K2);
+      const float arA = sr * (qt * K1);
+      const float arB = sr * fmaf(qdt, K1, fmaf(qt, K2, (1.f - 2.f * rt) * art * rdbB));
+      const float azA = sz * hmn;
+      const float azB = sz * ((hdp - ndot) + (1.f - 2.f * zt) * azt * hmn);
+      // ---- W_hh^T (primal dGH, tangent dGH) of the previous step ----
+      if (s > 0) {
+        mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((s - 1) >> 1) & 1));
+        if (tid == 0 && s + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);
+        float2 acc[G][2][2];          // [sequence][adjoint][output column]
+#pragma unroll
+        for (int b = 0; b < G; ++b)
+#pragma unroll
+          for (int v = 0; v < 2; ++v) acc[b][v][0] = acc[b][v][1] = make_float2(0.f, 0.f);
+        const uint32_t dc = dbuf_a + (uint32_t)((ppar * BT + grp * G) * 6 * HR) * 4u + 16u * (uint32_t)ql;
+#pragma unroll
+        for (int i = 0; i < J / 4; ++i)
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+#pragma unroll
+            for (int b = 0; b < G; ++b)
+#pragma unroll
+              for (int v = 0; v < 2; ++v) {
+                const float4 dv = lds_v4(dc + (uint32_t)((b * 6 + v * 3 + g) * HR) * 4u + (uint32_t)(i * L2) * 16u);
+                const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
+#pragma unroll
+                for (int o = 0; o < 2; ++o) {
+                  acc[b][v][o] = __ffma2_rn(wt[o][g][2 * i], d01, acc[b][v][o]);
+                  acc[b][v][o] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[b][v][o]);
+                }
+              }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          float u[L2];
+#pragma unroll
+          for (int o = 0; o < 2; ++o)
+#pragma unroll
+            for (int b = 0; b < G; ++b) u[o * G + b] = acc[b][v][o].x + acc[b][v][o].y;
+          reduce_scatter<L2>(u, ql);
+          if (v == 0) ch[grp] += u[0]; else chd[grp] += u[0];
+        }
+      }
+      const float hb = fhb + ch[grp];
+      const float hdb = fhdb + chd[grp];
+      const float arb = fmaf(arA, hb, arB * hdb);
+      const float azb = fmaf(azA, hb, azB * hdb);
+      const float anb = fmaf(K1, hb, K2 * hdb);
+      const float qb = fmaf(qA, hb, qB * hdb);
+      const float arb_d = ardB * hdb, azb_d = azA * hdb, anb_d = K1 * hdb, qdb = qA * hdb;
+      ch[grp] = fmaf(zt, hb, zdot * hdb);      // direct paths into h_{t-1} / hd_{t-1}; the mat-vec parts follow next step
+      chd[grp] = zt * hdb;
+      if (s + 1 < T) {
+        const uint32_t off = (uint32_t)((par * BT + grp * G) * 6 * HR) * 4u;
+        const float vals[6] = {arb, azb, qb, arb_d, azb_d, qdb};
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+          const float v0 = __shfl_sync(0xffffffffu, vals[e], srcl[0]), v1 = __shfl_sync(0xffffffffu, vals[e], srcl[1]),
+                      v2 = __shfl_sync(0xffffffffu, vals[e], srcl[2]), v3 = __shfl_sync(0xffffffffu, vals[e], srcl[3]);
+#pragma unroll
+          for (int d = 0; d < ND; ++d)
+            if (r_ok[d])
+              st_async_v4(r_d[d] + off + (uint32_t)(e * HR) * 4u, v0, v1, v2, v3, r_bar[d] + (uint32_t)(grp * 2 + par) * 8u);
+        }
+      }
+      float* so = sgw + ((grp * G + ob) * 8) * HU + kl;
+      so[0] = arb; so[HU] = azb; so[2 * HU] = anb; so[3 * HU] = qb;
+      so[4 * HU] = arb_d; so[5 * HU] = azb_d; so[6 * HU] = anb_d; so[7 * HU] = qdb;
+    }
+  }
+  __syncthreads();
+  store(0, T - 1);
+  cp_async_wait<0>();
+  cluster_sync_all();
+}
+
+template <int H, int CS, int NGRP>
+int launch_cl_jb(cudaStream_t st, const ClJbParams& p) {
+  using S = ClJbSmem<H, CS, NGRP>;
+  auto kern = gru_cl_jvp_bwd_kernel<H, CS, NGRP>;
+  TG_OPT_IN_SMEM(kern, "gru_cl_jvp_bwd");
+  const int clusters = (p.B + S::BT - 1) / S::BT;
+  kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
+  return tg_check_launch("gru_cl_jvp_bwd");
+}
+
 template <int H, int CS, int NGRP, int SG>
 int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
   using S = ClFwdSmem<H, CS, NGRP, SG>;
@@ -625,5 +889,23 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
     return (clusters1 * 8 <= sms) ? launch_cl_bwd<256, 8, 1>(st, p) : launch_cl_bwd<256, 8, 2>(st, p);
   }
   tg_set_error("gru_cl_bwd: hidden size %d not supported", H);
+  return TG_ERR_UNSUPPORTED;
+}
+
+// reverse-over-tangent at H = 128: the one-SM kernel (gru_jvp.cu) spills and takes 3.5 ms per call at the c3 shape
+bool tg_cluster_takes_jvp_bwd(int H, int B) {
+  (void)B;
+  return tg_use_cluster() != 0 && H == 128;
+}
+
+int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
+                      const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh, float* gib,
+                      float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only) {
+  ClJbParams p{hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, last_only};
+  if (H == 128) {
+    const int clusters1 = (B + 3) / 4;
+    return (clusters1 * 2 <= tg_num_sms()) ? launch_cl_jb<128, 2, 1>(st, p) : launch_cl_jb<128, 2, 2>(st, p);
+  }
+  tg_set_error("gru_cl_jvp_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }

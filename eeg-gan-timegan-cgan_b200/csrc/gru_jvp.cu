@@ -528,6 +528,13 @@ int tg_gru_jvp_bwd_impl(cudaStream_t st, const float* hbar, const float* hdbar, 
   TG_REQUIRE(hbar && hdbar && rzn && q && ta && qdot && y && ydot && whh && gib && qb && gidb && qdb, TG_ERR_ARG,
              "gru_jvp_bwd: null pointer");
   TG_REQUIRE(B > 0 && T > 0 && H > 0, TG_ERR_SHAPE, "gru_jvp_bwd: bad shape B=%d T=%d H=%d", B, T, H);
+  {
+    const int lo = (flags & TG_GRU_DY_LAST) ? 1 : 0;
+    if (tg_cluster_takes_jvp_bwd(H, B) && !(flags & TG_GRU_NO_BULK) && tg_aligned16(rzn) && tg_aligned16(q) &&
+        tg_aligned16(ta) && tg_aligned16(qdot) && tg_aligned16(y) && tg_aligned16(ydot) && tg_aligned16(gib) &&
+        tg_aligned16(qb) && tg_aligned16(gidb) && tg_aligned16(qdb) && (lo || (tg_aligned16(hbar) && tg_aligned16(hdbar))))
+      return tg_gru_cl_jvp_bwd(st, hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, H, lo);
+  }
   if (H > 128) {
     TG_REQUIRE(whh_t, TG_ERR_ARG, "gru_jvp_bwd: hidden size %d > 128 needs the transposed weight (w_hh_t)", H);
     return tg_bigh_jvp_bwd(st, hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh_t, gib, qb, gidb, qdb, B, T, H,

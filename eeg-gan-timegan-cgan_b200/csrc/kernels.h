@@ -43,6 +43,11 @@ int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh
 int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y, const float* whh,
                   float* dgi, float* dq, int B, int T, int H, int dy_last);
 
+bool tg_cluster_takes_jvp_bwd(int H, int B);
+int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
+                      const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh, float* gib,
+                      float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only);
+
 // time-batched contractions (FFMA baseline path; fp32 exact)
 int tg_gemm_nt_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
                     int ldc, int M, int N, int K, int accumulate);

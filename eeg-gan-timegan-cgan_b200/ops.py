@@ -376,7 +376,10 @@ def stack_jvp_backward(hbar_last: torch.Tensor, hdbar_last: torch.Tensor, saves:
         def _wg(gib=gib, qb=qb, gidb=gidb, qdb=qdb, sv=sv, ts=ts, g_wih=g_wih, g_whh=g_whh, g_bih=g_bih,
                 g_bhh=g_bhh, I=I):
             # primal path, then tangent path (no bias terms in the tangent)
-            wgrad_gru(gib, qb, sv.inp.reshape(B * T, I), sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
+            x2 = sv.inp.reshape(B * T, I + sv.ipad)
+            if sv.ipad:                      # a layer input that stack_forward carried zero-padded (pad_cols)
+                x2 = x2[:, :I].contiguous()
+            wgrad_gru(gib, qb, x2, sv.y, g_wih, g_whh, g_bih, g_bhh, accumulate)
             wgrad_gru(gidb, qdb, ts.xdot.reshape(B * T, I), ts.ydot, g_wih, g_whh, None, None, True)
         side.issue(_wg, gib, qb, gidb, qdb)
     side.join()

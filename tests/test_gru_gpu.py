@@ -194,7 +194,8 @@ def test_autograd_function_module_api():
 
 
 @pytest.mark.parametrize("B,T,I,H,L", [(3, 12, 5, 8, 2), (4, 64, 24, 24, 3), (2, 30, 14, 64, 1), (2, 20, 14, 128, 2),
-                                       (5, 16, 14, 256, 2)])
+                                       (5, 16, 14, 256, 2),
+                                       (301, 10, 14, 128, 2)])   # cluster reverse-over-tangent: two groups, ragged
 def test_tangent_forward_and_reverse_match_oracle(B, T, I, H, L):
     """R1 building blocks (train_timegan.py:198-202 restated per SURVEY.md A.4) vs oracle/gru_math.py in fp64."""
     from oracle import gru_math as gm
