@@ -154,33 +154,45 @@ def bce(p, y):
 # ------------------------------------------------------------------------------------------------
 # covariance + autocorrelation terms of gen_step
 # ------------------------------------------------------------------------------------------------
-def _moments(x2d, n_global_fn):
-    """mean (C,), centred copy, centred Gram (C,C) of a (rows,C) matrix; statistics over the global batch."""
-    rows, Cc = x2d.shape
-    s, n = _dist.allreduce_stats(ops.colsum(x2d), rows)
-    mean = (s / n).contiguous()
-    xc = torch.empty_like(x2d)
-    check(lib.tg_center_scale(stream_ptr(), ptr(x2d), ptr(mean), None, ptr(xc), rows, Cc), "tg_center_scale")
-    gram = torch.empty(Cc, Cc, dtype=torch.float32, device=x2d.device)
-    ops.wgrad(xc, xc, gram, None, Cc)
-    gram, _ = _dist.allreduce_stats(gram, rows)
-    return mean, xc, gram, n
+def _moments_pair(xa, xb):
+    """Centred copies and centred Grams (C,C) of TWO (rows,C) matrices (generated and real windows), statistics over
+    the global batch.  The two column sums travel in ONE statistics all-reduce, the two Grams in another: under data
+    parallelism every call site is a kernel launch plus an NVLink flag round trip on the forward's critical path."""
+    rows, Cc = xa.shape
+    sums = torch.cat([ops.colsum(xa), ops.colsum(xb)])
+    sums, n = _dist.allreduce_stats(sums, rows)
+    out = []
+    grams = torch.empty(2, Cc, Cc, dtype=torch.float32, device=xa.device)
+    for i, x2d in enumerate((xa, xb)):
+        mean = (sums[i * Cc:(i + 1) * Cc] / n).contiguous()
+        xc = torch.empty_like(x2d)
+        check(lib.tg_center_scale(stream_ptr(), ptr(x2d), ptr(mean), None, ptr(xc), rows, Cc), "tg_center_scale")
+        ops.wgrad(xc, xc, grams[i], None, Cc)
+        out.append(xc)
+    grams, _ = _dist.allreduce_stats(grams, rows)
+    return out[0], grams[0], out[1], grams[1], n
 
 
-def _acf_of(xc2d, gram, n, B, T, Cc, L):
-    std = torch.sqrt(torch.diagonal(gram) / (n - 1))
-    s = std + 1e-8
-    inv_s = (1.0 / s).contiguous()
-    zero = torch.zeros(Cc, dtype=torch.float32, device=xc2d.device)
-    xz = torch.empty_like(xc2d)
-    check(lib.tg_center_scale(stream_ptr(), ptr(xc2d), ptr(zero), ptr(inv_s), ptr(xz), B * T, Cc), "tg_center_scale")
-    part = torch.empty(B, L * Cc, dtype=torch.float32, device=xc2d.device)
-    check(lib.tg_acf_fwd(stream_ptr(), ptr(xz), B, T, Cc, L, ptr(part)), "tg_acf_fwd")
-    sums, Bg = _dist.allreduce_stats(ops.colsum(part), B)
-    lags = torch.arange(1, L + 1, device=xc2d.device, dtype=torch.float32)
+def _acf_pair(xc_a, gram_a, xc_b, gram_b, n, B, T, Cc, L):
+    """Lag-1..L autocorrelation tables of both (centred) tensors; the lagged-product sums share one all-reduce."""
+    dev = xc_a.device
+    zero = torch.zeros(Cc, dtype=torch.float32, device=dev)
+    parts, keep = [], []
+    for xc2d, gram in ((xc_a, gram_a), (xc_b, gram_b)):
+        std = torch.sqrt(torch.diagonal(gram) / (n - 1))
+        inv_s = (1.0 / (std + 1e-8)).contiguous()
+        xz = torch.empty_like(xc2d)
+        check(lib.tg_center_scale(stream_ptr(), ptr(xc2d), ptr(zero), ptr(inv_s), ptr(xz), B * T, Cc), "tg_center_scale")
+        part = torch.empty(B, L * Cc, dtype=torch.float32, device=dev)
+        check(lib.tg_acf_fwd(stream_ptr(), ptr(xz), B, T, Cc, L, ptr(part)), "tg_acf_fwd")
+        parts.append(ops.colsum(part))
+        keep.append((xz, std, inv_s))
+    sums, Bg = _dist.allreduce_stats(torch.cat(parts), B)
+    lags = torch.arange(1, L + 1, device=dev, dtype=torch.float32)
     denom = (Bg * (T - lags)).unsqueeze(1)                      # (L,1): B*(T-lag) samples per lag
-    acf = sums.view(L, Cc) / denom
-    return acf, xz, std, inv_s, denom
+    acf_a = sums[:L * Cc].view(L, Cc) / denom
+    acf_b = sums[L * Cc:].view(L, Cc) / denom
+    return acf_a, acf_b, keep[0], denom
 
 
 class _CovAcf(torch.autograd.Function):
@@ -193,8 +205,7 @@ class _CovAcf(torch.autograd.Function):
         B, T, Cc = x_gen.shape
         L = max(1, min(int(max_lag), T - 1))
         dev = x_gen.device
-        _, xc_g, gram_g, n = _moments(x_gen.view(B * T, Cc), None)
-        _, xc_r, gram_r, _ = _moments(x_real.view(B * T, Cc), None)
+        xc_g, gram_g, xc_r, gram_r, n = _moments_pair(x_gen.view(B * T, Cc), x_real.view(B * T, Cc))
         cov_term = torch.zeros((), device=dev)
         acf_term = torch.zeros((), device=dev)
         ctx.need_cov, ctx.need_acf = need_cov, need_acf
@@ -207,8 +218,7 @@ class _CovAcf(torch.autograd.Function):
             cov_term = fro / (float(Cc * Cc) ** 0.5)
             saved += [diff, fro]
         if need_acf:
-            acf_g, xz_g, std_g, inv_s_g, denom = _acf_of(xc_g, gram_g, n, B, T, Cc, L)
-            acf_r, _, _, _, _ = _acf_of(xc_r, gram_r, n, B, T, Cc, L)
+            acf_g, acf_r, (xz_g, std_g, inv_s_g), denom = _acf_pair(xc_g, gram_g, xc_r, gram_r, n, B, T, Cc, L)
             d = acf_g - acf_r
             acf_term = d.abs().mean()
             saved += [xz_g, std_g, inv_s_g, torch.sign(d) / denom / float(L * Cc)]
