@@ -308,12 +308,21 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         acc[b][2] = make_float2(0.f, 0.f);
       }
       const uint32_t hc = hbuf_a + (uint32_t)((ppar * BT + grp * SG) * HR) * 4u + 16u * (uint32_t)ql;
+      // operand fetches run one k-block ahead of the FFMA2s that consume them (two warps per scheduler cannot hide the
+      // shared-memory latency by themselves: short-scoreboard was the top stall of the mat-vec)
+      float4 hv[2][SG];
+#pragma unroll
+      for (int b = 0; b < SG; ++b) hv[0][b] = lds_v4(hc + (uint32_t)(b * HR) * 4u);
 #pragma unroll
       for (int i = 0; i < KS / 4; ++i) {
+        if (i + 1 < KS / 4) {
+#pragma unroll
+          for (int b = 0; b < SG; ++b)
+            hv[(i + 1) & 1][b] = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)((i + 1) * G) * 16u);
+        }
 #pragma unroll
         for (int b = 0; b < SG; ++b) {
-          const float4 hv = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)(i * G) * 16u);
-          const float2 h01 = make_float2(hv.x, hv.y), h23 = make_float2(hv.z, hv.w);
+          const float2 h01 = make_float2(hv[i & 1][b].x, hv[i & 1][b].y), h23 = make_float2(hv[i & 1][b].z, hv[i & 1][b].w);
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             acc[b][g] = __ffma2_rn(w[g][2 * i], h01, acc[b][g]);
@@ -500,20 +509,30 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 #pragma unroll
         for (int b = 0; b < G; ++b) acc[b][0] = acc[b][1] = make_float2(0.f, 0.f);
         const uint32_t dc = dbuf_a + (uint32_t)((ppar * BT + grp * G) * 3 * HR) * 4u + 16u * (uint32_t)ql;
+        // operand fetches run one (row block, gate) ahead of the FFMA2s that consume them
+        float4 dvv[2][G];
 #pragma unroll
-        for (int i = 0; i < J / 4; ++i)
+        for (int b = 0; b < G; ++b) dvv[0][b] = lds_v4(dc + (uint32_t)((b * 3) * HR) * 4u);
 #pragma unroll
-          for (int g = 0; g < 3; ++g)
+        for (int it = 0; it < 3 * (J / 4); ++it) {
+          const int i = it / 3, g = it % 3;
+          if (it + 1 < 3 * (J / 4)) {
+            const int i1 = (it + 1) / 3, g1 = (it + 1) % 3;
 #pragma unroll
-            for (int b = 0; b < G; ++b) {
-              const float4 dv = lds_v4(dc + (uint32_t)((b * 3 + g) * HR) * 4u + (uint32_t)(i * L2) * 16u);
-              const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
+            for (int b = 0; b < G; ++b)
+              dvv[(it + 1) & 1][b] = lds_v4(dc + (uint32_t)((b * 3 + g1) * HR) * 4u + (uint32_t)(i1 * L2) * 16u);
+          }
 #pragma unroll
-              for (int o = 0; o < 2; ++o) {
-                acc[b][o] = __ffma2_rn(wt[o][g][2 * i], d01, acc[b][o]);
-                acc[b][o] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[b][o]);
-              }
+          for (int b = 0; b < G; ++b) {
+            const float4 dv = dvv[it & 1][b];
+            const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              acc[b][o] = __ffma2_rn(wt[o][g][2 * i], d01, acc[b][o]);
+              acc[b][o] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[b][o]);
             }
+          }
+        }
         float v[L2];
 #pragma unroll
         for (int o = 0; o < 2; ++o)
