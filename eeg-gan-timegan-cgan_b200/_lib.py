@@ -32,6 +32,7 @@ SIGNATURES = {
     "tg_last_error": (C.c_char_p, []),
     "tg_device_sm_count": (_i, []),
     "tg_set_option": (_i, [C.c_char_p, _i]),
+    "tg_cluster_capacity": (_i, [_i, _i, _i]),
     "tg_launch_count": (_ll, []),
     "tg_prof_kinds": (_i, []),
     "tg_prof_kind_name": (C.c_char_p, [_i]),

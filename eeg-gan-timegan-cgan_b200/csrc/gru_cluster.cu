@@ -859,14 +859,82 @@ int launch_cl_bwd(cudaStream_t st, const ClBwdParams& p) {
   return tg_check_launch("gru_cl_bwd");
 }
 
+// How many clusters of a kernel can be resident at once (cudaOccupancyMaxActiveClusters): clusters are placed inside
+// one GPC, so an 8-CTA cluster does not simply get 148 / 8 slots.  A launch with more clusters than that runs in waves,
+// which for a persistent 768-step kernel doubles its time -- the group count per cluster is chosen so that ONE wave
+// covers the batch whenever the shared-memory budget allows.
+template <typename K>
+int max_active_clusters(K kern, int cs, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(cs * 64));
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+  return n;
+}
+
+struct ClCaps { int f128[2], b128[2], j128[2], f256[4], b256[2]; bool ready; };
+ClCaps& cl_caps() {
+  static ClCaps c = {};
+  if (!c.ready) {
+    // opt in to the shared memory first (the occupancy query honours the function attribute)
+    auto optin = [](auto kern) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tg_max_optin_smem()); };
+    optin(gru_cl_fwd_kernel<128, 2, 1, 4>); optin(gru_cl_fwd_kernel<128, 2, 2, 4>);
+    optin(gru_cl_bwd_kernel<128, 2, 1>); optin(gru_cl_bwd_kernel<128, 2, 2>);
+    optin(gru_cl_jvp_bwd_kernel<128, 2, 1>); optin(gru_cl_jvp_bwd_kernel<128, 2, 2>);
+    optin(gru_cl_fwd_kernel<256, 8, 1, 8>); optin(gru_cl_fwd_kernel<256, 8, 2, 8>);
+    optin(gru_cl_fwd_kernel<256, 8, 3, 8>); optin(gru_cl_fwd_kernel<256, 8, 4, 8>);
+    optin(gru_cl_bwd_kernel<256, 8, 1>); optin(gru_cl_bwd_kernel<256, 8, 2>);
+    c.f128[0] = max_active_clusters(gru_cl_fwd_kernel<128, 2, 1, 4>, 2, ClFwdSmem<128, 2, 1, 4>::bytes);
+    c.f128[1] = max_active_clusters(gru_cl_fwd_kernel<128, 2, 2, 4>, 2, ClFwdSmem<128, 2, 2, 4>::bytes);
+    c.b128[0] = max_active_clusters(gru_cl_bwd_kernel<128, 2, 1>, 2, ClBwdSmem<128, 2, 1>::bytes);
+    c.b128[1] = max_active_clusters(gru_cl_bwd_kernel<128, 2, 2>, 2, ClBwdSmem<128, 2, 2>::bytes);
+    c.j128[0] = max_active_clusters(gru_cl_jvp_bwd_kernel<128, 2, 1>, 2, ClJbSmem<128, 2, 1>::bytes);
+    c.j128[1] = max_active_clusters(gru_cl_jvp_bwd_kernel<128, 2, 2>, 2, ClJbSmem<128, 2, 2>::bytes);
+    c.f256[0] = max_active_clusters(gru_cl_fwd_kernel<256, 8, 1, 8>, 8, ClFwdSmem<256, 8, 1, 8>::bytes);
+    c.f256[1] = max_active_clusters(gru_cl_fwd_kernel<256, 8, 2, 8>, 8, ClFwdSmem<256, 8, 2, 8>::bytes);
+    c.f256[2] = max_active_clusters(gru_cl_fwd_kernel<256, 8, 3, 8>, 8, ClFwdSmem<256, 8, 3, 8>::bytes);
+    c.f256[3] = max_active_clusters(gru_cl_fwd_kernel<256, 8, 4, 8>, 8, ClFwdSmem<256, 8, 4, 8>::bytes);
+    c.b256[0] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 1>, 8, ClBwdSmem<256, 8, 1>::bytes);
+    c.b256[1] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 2>, 8, ClBwdSmem<256, 8, 2>::bytes);
+    c.ready = true;
+  }
+  return c;
+}
+
+// smallest group count (1-based index into caps) whose cluster count fits one wave; n if none does
+int pick_groups(int B, int seqs_per_group, const int* caps, int n) {
+  for (int g = 1; g <= n; ++g) {
+    const int clusters = (B + seqs_per_group * g - 1) / (seqs_per_group * g);
+    if (caps[g - 1] > 0 && clusters <= caps[g - 1]) return g;
+  }
+  return n;
+}
+
 }  // namespace
+
+// diagnostic: resident-cluster capacity of the (H, direction, groups) instantiation; 0 = unknown / not instantiated
+extern "C" int tg_cluster_capacity(int H, int backward, int groups) {
+  ClCaps& c = cl_caps();
+  if (H == 128 && groups >= 1 && groups <= 2) return backward == 2 ? c.j128[groups - 1] : (backward ? c.b128[groups - 1] : c.f128[groups - 1]);
+  if (H == 256 && !backward && groups >= 1 && groups <= 4) return c.f256[groups - 1];
+  if (H == 256 && backward == 1 && groups >= 1 && groups <= 2) return c.b256[groups - 1];
+  return 0;
+}
 
 // Which (hidden size, batch, direction) the cluster kernels take -- chosen from measurements on a B200 (tools/probe_cluster.py,
 // profiles/r02_probe_cluster.log; T = 768, us per layer pass, cluster vs. the kernel it replaces):
-//   H = 128  forward   B <= 296: 784 vs 747 (gru_fwd.cu, 512 threads, BT = 2)  -> legacy;   B = 512: 1489 vs 1561 -> cluster
+//   H = 128  forward   B <= 296: 766 vs 747 (gru_fwd.cu, 512 threads, BT = 2)  -> legacy;   B = 512: 1421 vs 1561 -> cluster
 //   H = 128  BPTT      B = 256: 1057 vs 1477,  B = 512: 2076 vs 2956                          -> cluster
-//   H = 256  forward   B = 128: 2841 vs 9381,  B = 256: 5513 vs 9413 (gru_bigh.cu, W_hh from L2) -> cluster
-//   H = 256  BPTT      B = 128: 4967 vs 7653 -> cluster;   B = 256 (two groups per cluster): 9281 vs 7690 -> gru_bigh.cu
+//   H = 256  forward   B = 256: 4131 (three groups per cluster, 11 clusters = one wave; 5513 with two groups = 16 clusters in
+//                      two waves: only 15 eight-CTA clusters are resident at once) vs 9429 (gru_bigh.cu, W_hh from L2)  -> cluster
+//   H = 256  BPTT      cluster when the batch fits one wave with <= 2 groups per cluster (shared-memory limit):
+//                      B = 128: 4603 vs 7703 -> cluster;  B = 256: 9184 (two waves) vs 7693 -> gru_bigh.cu
 // Exact sizes only: the k-slices are compile-time register arrays.  TIMEGAN_B200_CLUSTER=0 disables them, =2 forces them
 // for every H = 128 / 256 launch (tests).
 bool tg_cluster_takes(int H, int B, bool backward) {
@@ -875,21 +943,24 @@ bool tg_cluster_takes(int H, int B, bool backward) {
   if (mode == 2) return true;
   const int sms = tg_num_sms();
   if (H == 128) return backward || ((B + 3) / 4) * 2 > sms;
-  return !backward || ((B + 7) / 8) * 8 <= sms;
+  ClCaps& c = cl_caps();
+  if (!backward) return true;      // even in two waves it beats the L2-streaming kernel (5.5 vs 9.4 ms at B = 256)
+  const int g = pick_groups(B, 8, c.b256, 2);
+  return (B + 8 * g - 1) / (8 * g) <= c.b256[g - 1];
 }
 
-// Sequence groups per cluster: one group (G sequences) while every cluster is co-resident (one CTA per SM), two beyond.
 int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T, int H,
                   int save) {
   ClFwdParams p{gi, whh, bhh, y, q, B, T, save};
-  const int sms = tg_num_sms();
-  if (H == 128) {
-    const int clusters1 = (B + 3) / 4;
-    return (clusters1 * 2 <= sms) ? launch_cl_fwd<128, 2, 1, 4>(st, p) : launch_cl_fwd<128, 2, 2, 4>(st, p);
-  }
+  ClCaps& c = cl_caps();
+  if (H == 128) return pick_groups(B, 4, c.f128, 2) == 1 ? launch_cl_fwd<128, 2, 1, 4>(st, p) : launch_cl_fwd<128, 2, 2, 4>(st, p);
   if (H == 256) {
-    const int clusters1 = (B + 7) / 8;
-    return (clusters1 * 8 <= sms) ? launch_cl_fwd<256, 8, 1, 8>(st, p) : launch_cl_fwd<256, 8, 2, 8>(st, p);
+    switch (pick_groups(B, 8, c.f256, 4)) {
+      case 1: return launch_cl_fwd<256, 8, 1, 8>(st, p);
+      case 2: return launch_cl_fwd<256, 8, 2, 8>(st, p);
+      case 3: return launch_cl_fwd<256, 8, 3, 8>(st, p);
+      default: return launch_cl_fwd<256, 8, 4, 8>(st, p);
+    }
   }
   tg_set_error("gru_cl_fwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
@@ -898,15 +969,9 @@ int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh
 int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y, const float* whh,
                   float* dgi, float* dq, int B, int T, int H, int dy_last) {
   ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
-  const int sms = tg_num_sms();
-  if (H == 128) {
-    const int clusters1 = (B + 3) / 4;
-    return (clusters1 * 2 <= sms) ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
-  }
-  if (H == 256) {
-    const int clusters1 = (B + 7) / 8;
-    return (clusters1 * 8 <= sms) ? launch_cl_bwd<256, 8, 1>(st, p) : launch_cl_bwd<256, 8, 2>(st, p);
-  }
+  ClCaps& c = cl_caps();
+  if (H == 128) return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
+  if (H == 256) return pick_groups(B, 8, c.b256, 2) == 1 ? launch_cl_bwd<256, 8, 1>(st, p) : launch_cl_bwd<256, 8, 2>(st, p);
   tg_set_error("gru_cl_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }
@@ -921,10 +986,7 @@ int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, co
                       const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh, float* gib,
                       float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only) {
   ClJbParams p{hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, last_only};
-  if (H == 128) {
-    const int clusters1 = (B + 3) / 4;
-    return (clusters1 * 2 <= tg_num_sms()) ? launch_cl_jb<128, 2, 1>(st, p) : launch_cl_jb<128, 2, 2>(st, p);
-  }
+  if (H == 128) return pick_groups(B, 4, cl_caps().j128, 2) == 1 ? launch_cl_jb<128, 2, 1>(st, p) : launch_cl_jb<128, 2, 2>(st, p);
   tg_set_error("gru_cl_jvp_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }

@@ -49,6 +49,9 @@ int tg_device_sm_count(void);
  * CTAs (one per SM), leaving the other SMs to recurrent kernels issued on another stream; 0 = one CTA per SM.
  * Must not change between tg_wgrad_gru_workspace_bytes and the tg_wgrad_gru call that uses the workspace. */
 int tg_set_option(const char* key, int value);
+/* diagnostic: how many thread-block clusters of the H = 128 / 256 recurrent kernels (backward: 0 forward, 1 BPTT, 2 reverse-over-
+ * tangent; groups = sequence groups per cluster) can be resident at once on this device; 0 = no such instantiation */
+int tg_cluster_capacity(int H, int backward, int groups);
 
 /* ---- launch accounting and per-family device timing (measurement only; used by bench.py) -------------------
  * tg_launch_count: kernels launched by this library since load.  With tg_prof_enable(1) every call below is
