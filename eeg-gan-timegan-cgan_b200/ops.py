@@ -50,8 +50,32 @@ def set_bt_override(bt: int):
     _BT_OVERRIDE = bt
 
 
-def _flags(base: int = 0) -> int:
-    return base | (_BT_OVERRIDE << 8)
+# Sequences-per-CTA hint for passes that run BESIDE another recurrent pass (train_timegan._Fork regions): two concurrent
+# B = 256 launches with one sequence per CTA need 512 CTA slots where the SMs have 444, so the second launch trails the
+# first; with two sequences per CTA both fit (tools/probe_concurrency.py: 395 us for both against 462 us back to back).
+# 0 = no hint.  Experimental: enabled by TIMEGAN_B200_FORK_BT=2.
+_BT_HINT = 0
+_FORK_BT = int(__import__("os").environ.get("TIMEGAN_B200_FORK_BT", "0"))
+
+
+def set_fork_bt(bt: int):
+    global _FORK_BT
+    _FORK_BT = int(bt)
+
+
+def fork_begin():
+    global _BT_HINT
+    _BT_HINT = _FORK_BT
+
+
+def fork_end():
+    global _BT_HINT
+    _BT_HINT = 0
+
+
+def _flags(base: int = 0, hint: int = None) -> int:
+    bt = _BT_OVERRIDE or (_BT_HINT if hint is None else hint)
+    return base | (bt << 8)
 
 
 # Weight gradients off the critical path: nothing downstream of BPTT needs dW until clip + Adam, so the fused
@@ -419,6 +443,7 @@ class GRUStackFunction(torch.autograd.Function):
         wd = [w.detach() for w in weights]
         y, saves = stack_forward(x, wd, save=need, masks=masks)
         ctx.saves, ctx.weights, ctx.masks, ctx.last_only = saves, wd, masks, bool(last_only)
+        ctx.bt_hint = _BT_HINT
         return y[:, -1, :].contiguous() if last_only else y
 
     @staticmethod
@@ -426,8 +451,13 @@ class GRUStackFunction(torch.autograd.Function):
     def backward(ctx, dy):
         need_dx = ctx.needs_input_grad[0]
         need_dw = any(ctx.needs_input_grad[3:])
-        dx, grads = stack_backward(dy, ctx.saves, ctx.weights, need_dx, need_dw, dy_last=ctx.last_only,
-                                   masks=ctx.masks)
+        global _BT_HINT
+        old, _BT_HINT = _BT_HINT, ctx.bt_hint          # the BPTT of a forked forward runs beside its sibling's BPTT too
+        try:
+            dx, grads = stack_backward(dy, ctx.saves, ctx.weights, need_dx, need_dw, dy_last=ctx.last_only,
+                                       masks=ctx.masks)
+        finally:
+            _BT_HINT = old
         ctx.saves = None
         if not need_dw:
             grads = [None] * len(ctx.weights)

@@ -433,6 +433,7 @@ class _Fork:
     def __enter__(self):
         if self.side is not self.main:
             self.side.wait_stream(self.main)
+            ops.fork_begin()               # until join(): recurrent passes on both streams run beside each other
         self.ctx = torch.cuda.stream(self.side)
         self.ctx.__enter__()
         return self
@@ -443,6 +444,7 @@ class _Fork:
     def join(self):
         if self.side is not self.main:
             self.main.wait_stream(self.side)
+            ops.fork_end()
 
 
 def _as_float(t, sync):
