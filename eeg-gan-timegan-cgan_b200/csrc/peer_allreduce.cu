@@ -12,8 +12,11 @@
 //     with a system-scope release store over NVLink, waits for the peers' flag[c], then pulls chunk c from every
 //     rank's staging area and adds the W contributions in rank order -- the same order on every rank, so all
 //     ranks end up with bit-identical sums (clip + Adam then stay in lock step without a broadcast);
-//   * nothing else synchronises: no grid barrier, no co-residency requirement (CTA c only ever waits for CTA c
-//     of its peers, which waits for nothing), no host involvement -- so the launch is graph-capturable.
+//   * nothing else synchronises: no grid barrier, no host involvement -- so the launch is graph-capturable.  CTA c
+//     only ever waits for CTA c of its peers, which waits for nothing else.  The grid is capped at PR_MAX_GRID CTAs
+//     (4 per SM: every CTA of the launch can be resident at once); a CTA walks its chunks c, c + grid, c + 2 grid, ...
+//     in increasing order, the same order on every rank, so a large bucket (23 MB of gradients at H = 256 = 1 400
+//     chunks) does not rely on the order in which the hardware dispatches the CTAs of an oversubscribed grid.
 //   * the epoch of a call site lives in device memory and is advanced by the last CTA of each launch, so a
 //     replayed graph keeps counting.  Staging is double-buffered by epoch parity: a rank can only overwrite
 //     parity p again after every peer has signalled the epoch in between, i.e. has finished reading p.
@@ -30,7 +33,8 @@
 namespace {
 
 constexpr int PR_THREADS = 256;
-constexpr int PR_CHUNK = 4096;  // floats per CTA
+constexpr int PR_CHUNK = 4096;  // floats per chunk
+constexpr int PR_MAX_GRID = 592;   // 4 CTAs per SM on a 148-SM part: all of a launch's CTAs are co-resident
 
 struct PeerArgs {
   float* t[TG_MT_MAX];
@@ -68,70 +72,71 @@ __device__ __forceinline__ float4 ld_relaxed_sys_v4(const float* p) {
 }
 
 __global__ void __launch_bounds__(PR_THREADS) peer_allreduce_kernel(const __grid_constant__ PeerArgs a) {
-  const int c = blockIdx.x, tid = threadIdx.x;
-  int t = 0;
-  while (t + 1 < a.n && c >= a.blk_start[t + 1]) ++t;
-  const long long base = (long long)(c - a.blk_start[t]) * PR_CHUNK;
-  const int len = (int)min((long long)PR_CHUNK, a.size[t] - base);
-  float* __restrict__ tens = a.t[t] + base;
+  const int tid = threadIdx.x;
   const unsigned int e = *reinterpret_cast<volatile unsigned int*>(a.epoch) + 1u;
-  const size_t slot = (size_t)(e & 1u) * a.nchunks * PR_CHUNK + (size_t)c * PR_CHUNK;
-  float* mine = a.data[a.rank] + slot;
-  const bool vec = ((reinterpret_cast<uintptr_t>(tens) & 15u) == 0) && (len % 4 == 0);
-
-  // 1. stage this rank's contribution
-  if (vec) {
-    for (int i = tid * 4; i < len; i += PR_THREADS * 4)
-      *reinterpret_cast<float4*>(mine + i) = *reinterpret_cast<const float4*>(tens + i);
-  } else {
-    for (int i = tid; i < len; i += PR_THREADS) mine[i] = tens[i];
-  }
-  __threadfence_system();
-  __syncthreads();
-
-  // 2. publish to every peer, then wait for every peer's chunk c
   __shared__ int failed;
-  if (tid == 0) failed = 0;
-  __syncthreads();
-  if (tid < a.world && tid != a.rank) {
-    st_release_sys(a.flags[tid] + (size_t)c * a.world + a.rank, e);
-    const unsigned int* f = a.flags[a.rank] + (size_t)c * a.world + tid;
-    const long long t0 = clock64();
-    while ((int)(ld_acquire_sys(f) - e) < 0) {
-      if (clock64() - t0 > a.timeout_clk) {  // a peer is gone; report instead of hanging the device
-        atomicExch(a.status, 1u);
-        failed = 1;
-        break;
-      }
-      __nanosleep(64);
-    }
-  }
-  __syncthreads();
+  for (int c = blockIdx.x; c < a.nchunks; c += gridDim.x) {
+    int t = 0;
+    while (t + 1 < a.n && c >= a.blk_start[t + 1]) ++t;
+    const long long base = (long long)(c - a.blk_start[t]) * PR_CHUNK;
+    const int len = (int)min((long long)PR_CHUNK, a.size[t] - base);
+    float* __restrict__ tens = a.t[t] + base;
+    const size_t slot = (size_t)(e & 1u) * a.nchunks * PR_CHUNK + (size_t)c * PR_CHUNK;
+    float* mine = a.data[a.rank] + slot;
+    const bool vec = ((reinterpret_cast<uintptr_t>(tens) & 15u) == 0) && (len % 4 == 0);
 
-  // 3. pull and add in rank order (identical on every rank => bit-identical results everywhere); after a timeout
-  //    the staging slots of the missing peer hold the data of two epochs ago -- never sum those
-  if (failed) {
-    const float nan = __int_as_float(0x7fc00000);
-    for (int i = tid; i < len; i += PR_THREADS) tens[i] = nan;
-  } else if (vec) {
-    for (int i = tid * 4; i < len; i += PR_THREADS * 4) {
-      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int r = 0; r < a.world; ++r) {
-        const float4 v = ld_relaxed_sys_v4(a.data[r] + slot + i);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    // 1. stage this rank's contribution
+    if (vec) {
+      for (int i = tid * 4; i < len; i += PR_THREADS * 4)
+        *reinterpret_cast<float4*>(mine + i) = *reinterpret_cast<const float4*>(tens + i);
+    } else {
+      for (int i = tid; i < len; i += PR_THREADS) mine[i] = tens[i];
+    }
+    if (tid == 0) failed = 0;
+    __threadfence_system();
+    __syncthreads();
+
+    // 2. publish to every peer, then wait for every peer's chunk c
+    if (tid < a.world && tid != a.rank) {
+      st_release_sys(a.flags[tid] + (size_t)c * a.world + a.rank, e);
+      const unsigned int* f = a.flags[a.rank] + (size_t)c * a.world + tid;
+      const long long t0 = clock64();
+      while ((int)(ld_acquire_sys(f) - e) < 0) {
+        if (clock64() - t0 > a.timeout_clk) {  // a peer is gone; report instead of hanging the device
+          atomicExch(a.status, 1u);
+          failed = 1;
+          break;
+        }
+        __nanosleep(64);
       }
-      *reinterpret_cast<float4*>(tens + i) = s;
     }
-  } else {
-    for (int i = tid; i < len; i += PR_THREADS) {
-      float s = 0.f;
-      for (int r = 0; r < a.world; ++r) s += ld_relaxed_sys(a.data[r] + slot + i);
-      tens[i] = s;
+    __syncthreads();
+
+    // 3. pull and add in rank order (identical on every rank => bit-identical results everywhere); after a timeout
+    //    the staging slots of the missing peer hold the data of two epochs ago -- never sum those
+    if (failed) {
+      const float nan = __int_as_float(0x7fc00000);
+      for (int i = tid; i < len; i += PR_THREADS) tens[i] = nan;
+    } else if (vec) {
+      for (int i = tid * 4; i < len; i += PR_THREADS * 4) {
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < a.world; ++r) {
+          const float4 v = ld_relaxed_sys_v4(a.data[r] + slot + i);
+          s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+        }
+        *reinterpret_cast<float4*>(tens + i) = s;
+      }
+    } else {
+      for (int i = tid; i < len; i += PR_THREADS) {
+        float s = 0.f;
+        for (int r = 0; r < a.world; ++r) s += ld_relaxed_sys(a.data[r] + slot + i);
+        tens[i] = s;
+      }
     }
+    __syncthreads();        // `failed` is rewritten by the next chunk
   }
 
   // 4. the last CTA of the launch advances the call site's epoch
-  __syncthreads();
   if (tid == 0) {
     __threadfence();
     const unsigned int done = atomicAdd(a.epoch + 1, 1u);
@@ -225,7 +230,7 @@ int tg_peer_allreduce(void* stream, int rank, int world, void* const* regions, s
   a.status = status;
   a.rank = rank; a.world = world; a.nchunks = blk;
   a.timeout_clk = (long long)tg_peer_timeout_ms() * 2000000LL;      // ~2 GHz SM clock
-  peer_allreduce_kernel<<<blk, PR_THREADS, 0, (cudaStream_t)stream>>>(a);
+  peer_allreduce_kernel<<<blk < PR_MAX_GRID ? blk : PR_MAX_GRID, PR_THREADS, 0, (cudaStream_t)stream>>>(a);
   return tg_check_launch("peer_allreduce");
 }
 

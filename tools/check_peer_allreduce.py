@@ -21,7 +21,9 @@ def main():
     assert pc is not None, "peer comm not enabled"
     ok = True
     g = torch.Generator(device=dev).manual_seed(100 + rank)
-    sizes = [1, 3, 4, 17, 4096, 4097, 12288, 100001, 290830]
+    # the last one is a 24 MB bucket (the H = 256 model's gradients): 1 465 chunks, more than the kernel's grid cap, so
+    # every CTA walks several chunks
+    sizes = [1, 3, 4, 17, 4096, 4097, 12288, 100001, 290830, 6000000]
     for rep in range(6):
         D.begin_step("T")
         base = [torch.randn(n + 1, generator=g, device=dev) for n in sizes]
