@@ -354,18 +354,19 @@ struct ClBwdParams {
   int B, T, dy_last;
 };
 
-template <int H, int CS, int NGRP>
+// PF = depth of the input ring (prefetch distance PF-1 steps); 2 where three groups per cluster leave no room for 4
+template <int H, int CS, int NGRP, int PF = CL_PF>
 struct ClBwdSmem {
   static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
   static constexpr int DBUF = 2 * BT * 3 * HR;         // floats: dGH vectors, double-buffered
-  static constexpr int RING = CL_PF * BT * 6 * HU;     // r,z,n,q,h_{t-1},dy
+  static constexpr int RING = PF * BT * 6 * HU;        // r,z,n,q,h_{t-1},dy
   static constexpr int STG = 2 * BT * 4 * HU;          // dar,daz,dan,dq
   static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
 };
 
-template <int H, int CS, int NGRP>
+template <int H, int CS, int NGRP, int PF = CL_PF>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams p) {
-  using S = ClBwdSmem<H, CS, NGRP>;
+  using S = ClBwdSmem<H, CS, NGRP, PF>;
   constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR;
   constexpr int L2 = 2 * G;            // lanes per output pair
   constexpr int J = H / L2;            // j values per lane and gate
@@ -425,7 +426,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   }
   auto prefetch = [&](int t) {         // t counts down; t < 0: nothing to load
     if (t >= 0) {
-      const uint32_t so = (uint32_t)(t % CL_PF) * SLOT_BYTES;
+      const uint32_t so = (uint32_t)(t % PF) * SLOT_BYTES;
 #pragma unroll
       for (int m = 0; m < NLD; ++m)
         if (lv[m] && !(lshift[m] && t == 0)) cp_async16(ls[m] + so, lp[m] + (size_t)t * lst[m]);
@@ -438,7 +439,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     for (int m = 0; m < NSD; ++m)
       if (sv[m]) *reinterpret_cast<float4*>(sp[m] + (size_t)t * sst[m]) = lds_v4(ss[m] + so);
   };
-  for (int s = 0; s < CL_PF - 1; ++s) prefetch(T - 1 - s);
+  for (int s = 0; s < PF - 1; ++s) prefetch(T - 1 - s);
 
   // =============================== compute warps ===============================
   // ---- W_hh^T slices: wt[o][g][m] = (W[gH+jj][k0+o], W[gH+jj+1][k0+o]),  jj = (i*L2+ql)*4 + 2*(m&1), i = m>>1 ----
@@ -485,16 +486,16 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 
   for (int s = 0; s < T; ++s) {
     const int t = T - 1 - s;
-    cp_async_wait<CL_PF - 2>();
+    cp_async_wait<PF - 2>();
     __syncthreads();
     if (s > 0) store(t + 1, s - 1);      // outputs of step t+1
-    prefetch(t - (CL_PF - 1));
+    prefetch(t - (PF - 1));
     const int par = s & 1, ppar = par ^ 1;
     float* sgw = stg + par * (BT * 4 * HU);
 #pragma unroll
     for (int grp = 0; grp < NGRP; ++grp) {
       // saved activations of (b, t, k): everything that does not depend on the carried dh first
-      const float* rg = ring + (((t % CL_PF) * BT + grp * G + ob) * 6) * HU + kl;
+      const float* rg = ring + (((t % PF) * BT + grp * G + ob) * 6) * HU + kl;
       const float r = rg[0], z = rg[HU], n = rg[2 * HU], qv = rg[3 * HU], dyv = rg[5 * HU];
       const float hp = (t == 0) ? 0.f : rg[4 * HU];          // h_{-1} = 0 (row -1 is never loaded; the slot is stale)
       const float omz = 1.f - z;
@@ -849,10 +850,10 @@ int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
   return tg_check_launch("gru_cl_fwd");
 }
 
-template <int H, int CS, int NGRP>
+template <int H, int CS, int NGRP, int PF = CL_PF>
 int launch_cl_bwd(cudaStream_t st, const ClBwdParams& p) {
-  using S = ClBwdSmem<H, CS, NGRP>;
-  auto kern = gru_cl_bwd_kernel<H, CS, NGRP>;
+  using S = ClBwdSmem<H, CS, NGRP, PF>;
+  auto kern = gru_cl_bwd_kernel<H, CS, NGRP, PF>;
   TG_OPT_IN_SMEM(kern, "gru_cl_bwd");
   const int clusters = (p.B + S::BT - 1) / S::BT;
   kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
@@ -878,7 +879,7 @@ int max_active_clusters(K kern, int cs, size_t smem) {
   return n;
 }
 
-struct ClCaps { int f128[2], b128[2], j128[2], f256[4], b256[2]; bool ready; };
+struct ClCaps { int f128[2], b128[2], j128[2], f256[4], b256[3]; bool ready; };
 ClCaps& cl_caps() {
   static ClCaps c = {};
   if (!c.ready) {
@@ -889,7 +890,7 @@ ClCaps& cl_caps() {
     optin(gru_cl_jvp_bwd_kernel<128, 2, 1>); optin(gru_cl_jvp_bwd_kernel<128, 2, 2>);
     optin(gru_cl_fwd_kernel<256, 8, 1, 8>); optin(gru_cl_fwd_kernel<256, 8, 2, 8>);
     optin(gru_cl_fwd_kernel<256, 8, 3, 8>); optin(gru_cl_fwd_kernel<256, 8, 4, 8>);
-    optin(gru_cl_bwd_kernel<256, 8, 1>); optin(gru_cl_bwd_kernel<256, 8, 2>);
+    optin(gru_cl_bwd_kernel<256, 8, 1>); optin(gru_cl_bwd_kernel<256, 8, 2>); optin(gru_cl_bwd_kernel<256, 8, 3, 2>);
     c.f128[0] = max_active_clusters(gru_cl_fwd_kernel<128, 2, 1, 4>, 2, ClFwdSmem<128, 2, 1, 4>::bytes);
     c.f128[1] = max_active_clusters(gru_cl_fwd_kernel<128, 2, 2, 4>, 2, ClFwdSmem<128, 2, 2, 4>::bytes);
     c.b128[0] = max_active_clusters(gru_cl_bwd_kernel<128, 2, 1>, 2, ClBwdSmem<128, 2, 1>::bytes);
@@ -902,6 +903,7 @@ ClCaps& cl_caps() {
     c.f256[3] = max_active_clusters(gru_cl_fwd_kernel<256, 8, 4, 8>, 8, ClFwdSmem<256, 8, 4, 8>::bytes);
     c.b256[0] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 1>, 8, ClBwdSmem<256, 8, 1>::bytes);
     c.b256[1] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 2>, 8, ClBwdSmem<256, 8, 2>::bytes);
+    c.b256[2] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 3, 2>, 8, ClBwdSmem<256, 8, 3, 2>::bytes);
     c.ready = true;
   }
   return c;
@@ -923,7 +925,7 @@ extern "C" int tg_cluster_capacity(int H, int backward, int groups) {
   ClCaps& c = cl_caps();
   if (H == 128 && groups >= 1 && groups <= 2) return backward == 2 ? c.j128[groups - 1] : (backward ? c.b128[groups - 1] : c.f128[groups - 1]);
   if (H == 256 && !backward && groups >= 1 && groups <= 4) return c.f256[groups - 1];
-  if (H == 256 && backward == 1 && groups >= 1 && groups <= 2) return c.b256[groups - 1];
+  if (H == 256 && backward == 1 && groups >= 1 && groups <= 3) return c.b256[groups - 1];
   return 0;
 }
 
@@ -933,8 +935,9 @@ extern "C" int tg_cluster_capacity(int H, int backward, int groups) {
 //   H = 128  BPTT      B = 256: 1057 vs 1477,  B = 512: 2076 vs 2956                          -> cluster
 //   H = 256  forward   B = 256: 4131 (three groups per cluster, 11 clusters = one wave; 5513 with two groups = 16 clusters in
 //                      two waves: only 15 eight-CTA clusters are resident at once) vs 9429 (gru_bigh.cu, W_hh from L2)  -> cluster
-//   H = 256  BPTT      cluster when the batch fits one wave with <= 2 groups per cluster (shared-memory limit):
-//                      B = 128: 4603 vs 7703 -> cluster;  B = 256: 9184 (two waves) vs 7693 -> gru_bigh.cu
+//   H = 256  BPTT      cluster when the batch fits one wave with <= 3 groups per cluster (shared-memory limit; the third
+//                      group costs the input ring two of its four stages): B = 128: 4603 vs 7703, B = 256: see
+//                      profiles/r02_probe_cluster.log; two groups = 16 clusters = two waves took 9184 vs 7693 (gru_bigh.cu)
 // Exact sizes only: the k-slices are compile-time register arrays.  TIMEGAN_B200_CLUSTER=0 disables them, =2 forces them
 // for every H = 128 / 256 launch (tests).
 bool tg_cluster_takes(int H, int B, bool backward) {
@@ -945,7 +948,7 @@ bool tg_cluster_takes(int H, int B, bool backward) {
   if (H == 128) return backward || ((B + 3) / 4) * 2 > sms;
   ClCaps& c = cl_caps();
   if (!backward) return true;      // even in two waves it beats the L2-streaming kernel (5.5 vs 9.4 ms at B = 256)
-  const int g = pick_groups(B, 8, c.b256, 2);
+  const int g = pick_groups(B, 8, c.b256, 3);
   return (B + 8 * g - 1) / (8 * g) <= c.b256[g - 1];
 }
 
@@ -971,7 +974,13 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
   ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
   ClCaps& c = cl_caps();
   if (H == 128) return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
-  if (H == 256) return pick_groups(B, 8, c.b256, 2) == 1 ? launch_cl_bwd<256, 8, 1>(st, p) : launch_cl_bwd<256, 8, 2>(st, p);
+  if (H == 256) {
+    switch (pick_groups(B, 8, c.b256, 3)) {
+      case 1: return launch_cl_bwd<256, 8, 1>(st, p);
+      case 2: return launch_cl_bwd<256, 8, 2>(st, p);
+      default: return launch_cl_bwd<256, 8, 3, 2>(st, p);     // 218 KB of shared memory: a 2-deep input ring
+    }
+  }
   tg_set_error("gru_cl_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }

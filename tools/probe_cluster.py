@@ -5,7 +5,7 @@ from timegan_b200 import ops, _lib
 from timegan_b200._lib import lib
 dev='cuda'
 torch.zeros(1, device=dev)
-print('resident-cluster capacity: H=128 fwd', [lib.tg_cluster_capacity(128,0,g) for g in (1,2)], 'bwd', [lib.tg_cluster_capacity(128,1,g) for g in (1,2)], 'jvp', [lib.tg_cluster_capacity(128,2,g) for g in (1,2)], '| H=256 fwd', [lib.tg_cluster_capacity(256,0,g) for g in (1,2,3,4)], 'bwd', [lib.tg_cluster_capacity(256,1,g) for g in (1,2)], flush=True)
+print('resident-cluster capacity: H=128 fwd', [lib.tg_cluster_capacity(128,0,g) for g in (1,2)], 'bwd', [lib.tg_cluster_capacity(128,1,g) for g in (1,2)], 'jvp', [lib.tg_cluster_capacity(128,2,g) for g in (1,2)], '| H=256 fwd', [lib.tg_cluster_capacity(256,0,g) for g in (1,2,3,4)], 'bwd', [lib.tg_cluster_capacity(256,1,g) for g in (1,2,3)], flush=True)
 for H,B in [(128,256),(128,296),(128,512),(256,256),(256,128)]:
     T=768
     w=[torch.randn(3*H,H,device=dev)/H**0.5, torch.randn(3*H,H,device=dev)/H**0.5, torch.zeros(3*H,device=dev), torch.zeros(3*H,device=dev)]
