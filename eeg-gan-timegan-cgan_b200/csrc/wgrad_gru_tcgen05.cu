@@ -15,6 +15,8 @@
 // TMEM holds 512 accumulator columns: MT M-tiles x (I+H padded) columns.  When the whole [dGI | dq] operand does not fit
 // (H = 128: 4 M-tiles x 256 columns), the layer is done in several launches, each owning a range of M-tiles (i.e. of
 // dGI / dq columns) and streaming only those columns plus x and y; all launches write disjoint parts of one workspace.
+// When [x | y] is wider than one MMA's 256 columns (H = 256: 512), the accumulator columns are split into ranges of
+// <= 8 chunks as well: (M-tile range) x (column range) launches, each streaming its two operand slices.
 #include "tc_common.cuh"
 #include "kernels.h"
 
@@ -35,6 +37,7 @@ struct WlParams {
   int a1ch, a2ch;   // 32-col chunks of x (0 when x is absent) / y
   int MT, tmem_cols;
   int mt0;          // first M-tile (128 rows of [dGI | dq]^T) of this launch; it covers MT tiles
+  int ab, acnt;     // first 32-column chunk of [x | y] of this launch and how many it covers
 };
 
 template <int PASSES>
@@ -47,7 +50,7 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
   const int GTOT = p.g1ch + p.g2ch;                       // chunks of the whole [dGI | dq] operand
   const int cbase = p.mt0 * 4;                            // first chunk of this launch
   const int GCH = min(GTOT, cbase + p.MT * 4) - cbase;    // chunks of this launch
-  const int ACH = p.a1ch + p.a2ch;
+  const int ACH = p.acnt;                                 // [x | y] chunks of this launch: global chunks ab .. ab+acnt-1
   const int chunk_bytes = R * 128;
   const int stage_bytes = (GCH + ACH) * chunk_bytes;
   unsigned char* lo_base = smem + (size_t)NS * stage_bytes;                    // [2][stage_bytes] (3-pass only)
@@ -96,8 +99,11 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
           if (cg < p.g1ch) tma_load_2d(dst + c * chunk_bytes, &tmG1, &full[s], cg * 32, r0);
           else tma_load_2d(dst + c * chunk_bytes, &tmG2, &full[s], (cg - p.g1ch) * 32, r0);
         }
-        for (int k = 0; k < p.a1ch; ++k, ++c) tma_load_2d(dst + c * chunk_bytes, &tmA1, &full[s], k * 32, r0);
-        for (int k = 0; k < p.a2ch; ++k, ++c) tma_load_2d(dst + c * chunk_bytes, &tmA2, &full[s], k * 32, r0 - 1);
+        for (int k = 0; k < ACH; ++k, ++c) {
+          const int ca = p.ab + k;
+          if (ca < p.a1ch) tma_load_2d(dst + c * chunk_bytes, &tmA1, &full[s], ca * 32, r0);
+          else tma_load_2d(dst + c * chunk_bytes, &tmA2, &full[s], (ca - p.a1ch) * 32, r0 - 1);
+        }
       }
     }
     __syncwarp();
@@ -159,7 +165,7 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const int c = c0 + i;
+          const int c = p.ab * 32 + c0 + i;                  // column of the whole [x | y] operand
           if (c < ycol0) {                                   // x block -> dW_ih
             if (n < 3 * H && c < I) w_ih[(size_t)n * I + c] = v[i];
           } else {                                           // y block -> dW_hh
@@ -205,7 +211,7 @@ tc_wgrad_layer_kernel(const __grid_constant__ CUtensorMap tmG1, const __grid_con
         // in-place stores by itself), then column sums / h_{-1} zeroing / TF32 split, then the stores
         auto finish = [&](int c, int ci, float4 a) {
           if (c < GCH) { colsum[ci & 7].x += a.x; colsum[ci & 7].y += a.y; colsum[ci & 7].z += a.z; colsum[ci & 7].w += a.w; }
-          const bool kill = boundary && c >= GCH + p.a1ch;     // y row that belongs to the previous sequence
+          const bool kill = boundary && c >= GCH && (c - GCH + p.ab) >= p.a1ch;     // y row of the previous sequence
           if (kill) a = make_float4(0.f, 0.f, 0.f, 0.f);
           float4* ptr = reinterpret_cast<float4*>(base + (size_t)c * chunk_bytes + off);
           if (PASSES == 3) {
@@ -327,23 +333,26 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
   const int g1ch = (3 * H + 31) / 32, g2ch = (H + 31) / 32, a1ch = x ? (I + 31) / 32 : 0, a2ch = (H + 31) / 32;
   const int GCH = g1ch + g2ch, ACH = a1ch + a2ch, MT = (GCH + 3) / 4;
   const bool ok = (H % 4 == 0) && (!x || (ldx % 4 == 0 && tg_aligned16(x))) && tg_aligned16(dgi) && tg_aligned16(dq) &&
-                  tg_aligned16(y) && GCH <= WL_MAXCH && ACH * 32 <= 256 && M >= 256 && Mll < (1ll << 31);
+                  tg_aligned16(y) && M >= 256 && Mll < (1ll << 31);
   if (!ok) { tg_set_error("wgrad_gru: shape/alignment not supported by the fused tensor-core tile"); return TG_ERR_UNSUPPORTED; }
   const int Iw = x ? I : 0;
   TG_REQUIRE(ws_bytes >= tg_wgrad_gru_ws_bytes(M, Iw, H), TG_ERR_ARG, "wgrad_gru: workspace too small");
-  // M-tiles per launch: what 512 TMEM columns hold next to each other (all of them up to H = 96; two at H = 128)
-  int MTL = 512 / (ACH * 32);
+  // accumulator columns per launch: one MMA takes N <= 256 = 8 chunks of [x | y]
+  const int ACL = ACH < 8 ? ACH : 8;
+  // M-tiles per launch: what 512 TMEM columns hold next to each other (all of them up to H = 96; two at H >= 128)
+  int MTL = 512 / (ACL * 32);
   if (MTL > MT) MTL = MT;
+  if (MTL * 4 > WL_MAXCH) MTL = WL_MAXCH / 4;
   const int gch_l = (MTL * 4 < GCH) ? MTL * 4 : GCH;      // widest chunk range of a launch
   int R = 32, nstage = 0;
   for (; R >= 8; R >>= 1) {
-    const int stage_bytes = (gch_l + ACH) * R * 128;
+    const int stage_bytes = (gch_l + ACL) * R * 128;
     nstage = (tg_gemm_smem_budget() - WL_TAIL - 4 * R * 128) / stage_bytes - (passes == 3 ? WL_NLO : 0);
     if (nstage >= 4) break;
   }
   if (R < 8 || nstage < 3) { tg_set_error("wgrad_gru: tile does not fit shared memory"); return TG_ERR_UNSUPPORTED; }
   if (nstage > 8) nstage = 8;
-  const int stage_bytes = (gch_l + ACH) * R * 128;
+  const int stage_bytes = (gch_l + ACL) * R * 128;
   size_t smem = (size_t)(nstage + (passes == 3 ? WL_NLO : 0)) * stage_bytes + WL_TAIL + 4 * (size_t)R * 128;
   if (smem < (size_t)16 * gch_l * 32 * 4 + WL_TAIL) smem = (size_t)16 * gch_l * 32 * 4 + WL_TAIL;
 
@@ -359,9 +368,11 @@ int tg_wgrad_gru_tc_impl(cudaStream_t st, const float* dgi, const float* dq, con
   const int splits = wl_splits(M);
   int rows_per = (M + splits - 1) / splits;
   rows_per = (rows_per + R - 1) / R * R;
-  for (int mt0 = 0; mt0 < MT; mt0 += MTL) {
+  for (int mt0 = 0; mt0 < MT; mt0 += MTL)
+  for (int ab = 0; ab < ACH; ab += ACL) {
     const int mtl = (MT - mt0 < MTL) ? MT - mt0 : MTL;
-    WlParams p{ws, M, Iw, H, T, R, nstage, rows_per, g1ch, g2ch, a1ch, a2ch, mtl, pow2c(mtl * ACH * 32), mt0};
+    const int acnt = (ACH - ab < ACL) ? ACH - ab : ACL;
+    WlParams p{ws, M, Iw, H, T, R, nstage, rows_per, g1ch, g2ch, a1ch, a2ch, mtl, pow2c(mtl * acnt * 32), mt0, ab, acnt};
     if (passes == 3) {
       TG_OPT_IN_SMEM(tc_wgrad_layer_kernel<3>, "wgrad_gru");
       tc_wgrad_layer_kernel<3><<<splits, WL_THREADS, smem, st>>>(tmG1, tmG2, tmA1, tmA2, p);

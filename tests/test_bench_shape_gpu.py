@@ -53,12 +53,12 @@ def test_stack_forward_and_bptt_at_benchmark_shape(name, B, I, H, dy_last):
     _stack_parity(B, I, H, 3, dy_last, seed=B + H)
 
 
-@pytest.mark.parametrize("H,I", [(64, 64), (64, 14), (128, 128)])
-def test_fused_weight_gradient_at_m_196608(H, I):
+@pytest.mark.parametrize("H,I,B", [(64, 64, 256), (64, 14, 256), (128, 128, 256), (256, 256, 40), (256, 16, 40)])
+def test_fused_weight_gradient_at_m_196608(H, I, B):
     """tg_wgrad_gru (one launch per layer, split-M over every SM) at M = B*T = 196 608 against fp64 contractions:
     dW_ih = dGI^T x, dW_hh = [dGI_r, dGI_z, dq]^T h_{t-1}, db_ih = colsum dGI, db_hh = colsum [dGI_r, dGI_z, dq]."""
     from timegan_b200 import ops
-    B, T = 256, T_LEN
+    T = T_LEN                      # B = 256 -> M = 196 608; H = 256 (8 launches: 4 M-tile ranges x 2 column ranges) at M = 30 720
     g = torch.Generator().manual_seed(H + I)
     dgi = torch.randn(B, T, 3 * H, generator=g)
     dq = torch.randn(B, T, H, generator=g)
