@@ -26,16 +26,21 @@ def main():
         D.init(backend="nccl", device=dev)
     ops.set_proj_mode(a.proj)
     B, T = a.batch, 768
-    xs = [torch.rand(B, T, 14, device=dev) for _ in range(4)]
+    xs = [torch.rand(B, T, 14, device=dev) for _ in range(4)]        # per-rank batches for the step functions
+    # the scheduled phases shard the batch they are given (dist.shard_batch), like train_single_npz: give them the
+    # GLOBAL batch (B * world sequences, identical on every rank) so that every GPU still works on B sequences
+    gq = torch.Generator(device=dev).manual_seed(7)
+    xg = [torch.rand(B * world, T, 14, device=dev, generator=gq) for _ in range(2)] if world > 1 else xs
 
-    def timed(fn):
+    def timed(fn, data=None):
+        data = xs if data is None else data
         for i in range(3):
-            fn(xs[i % 4])
+            fn(data[i % len(data)])
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(a.steps):
-            fn(xs[i % 4])
+            fn(data[i % len(data)])
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / a.steps
@@ -49,8 +54,8 @@ def main():
         oD = tg.FusedAdam(m.discriminator.parameters(), lr=2e-4, betas=(0.5, 0.9))
         oG = tg.FusedAdam(P(m.generator, m.supervisor, m.embedder, m.recovery), lr=1e-3, betas=(0.5, 0.9))
         log = lambda s: None
-        ae = timed(lambda x: tt.phase_autoencoder(m, [(x,)], dev, oER, 0.5, 1, log))
-        sup = timed(lambda x: tt.phase_supervisor(m, [(x,)], dev, oS, 0.5, 1, log))
+        ae = timed(lambda x: tt.phase_autoencoder(m, [(x,)], dev, oER, 0.5, 1, log), xg)
+        sup = timed(lambda x: tt.phase_supervisor(m, [(x,)], dev, oS, 0.5, 1, log), xg)
 
         def joint(x):
             tt.disc_step(m, x, dev, oD, 0.2, 0.3, 0.5, None, 1.0, target_acc=0.525, band=0.15, sync=False)
