@@ -330,9 +330,9 @@ class BestSnapshot:
                                         ptr(val), ptr(self.best), ptr(self.best_step), float(step)),
               "tg_snapshot_if_better")
 
-    def checkpoint(self, best_step: int, now_step: int, meta: Dict, lr_at) -> Dict:
-        """The checkpoint dict of the snapshot (schema of tt:58-61).  `now_step` is the step the live optimisers are
-        at; their per-parameter `step` counters are rewound by (now_step - best_step); `lr_at(name, step)` gives the
+    def checkpoint(self, best_step: int, rewind: int, meta: Dict, lr_at) -> Dict:
+        """The checkpoint dict of the snapshot (schema of tt:58-61).  `rewind` = optimiser updates performed since the
+        snapshot was taken: the live per-parameter `step` counters are rewound by it; `lr_at(name, step)` gives the
         scheduled learning rate of optimiser `name` after `step` GAN steps."""
         snap = dict(zip(self.model_keys, self.dst[:self.n_model]))
         model_sd = type(self.model.state_dict())((k, snap.get(k, v)) for k, v in self.model.state_dict().items())
@@ -348,7 +348,7 @@ class BestSnapshot:
                     if st:
                         st["exp_avg"] = moments[(name, id(p), "exp_avg")]
                         st["exp_avg_sq"] = moments[(name, id(p), "exp_avg_sq")]
-                        st["step"] = torch.tensor(float(st["step"]) - float(now_step - best_step), dtype=torch.float32)
+                        st["step"] = torch.tensor(float(st["step"]) - float(rewind), dtype=torch.float32)
                         sd["state"][idx] = st
                     idx += 1
             out[name] = sd
@@ -856,6 +856,7 @@ def train_single_npz(npz_path: Path, out_dir: Path,
     target = 0.5 * (d_min_acc + d_max_acc)
     band = max(0.0, d_max_acc - d_min_acc)
     pending = []   # (step, device scalars) awaiting a flush
+    skipped = []   # GAN steps without an optimiser update (data-parallel batches smaller than the world size)
     snap = BestSnapshot(model, optG, optD, device, best_ckpt_loss) if rank0 else None
     graphed = None
     if use_graph:
@@ -891,7 +892,8 @@ def train_single_npz(npz_path: Path, out_dir: Path,
             if best_step >= 0 and best_step != snap.written_step:
                 # tt:410-413: the weights after the step with the lowest g_total so far -- captured on the device at
                 # that step, written now (behind the training stream)
-                best_saver.save_state(best_path, snap.checkpoint(best_step, now_step, meta, lr_at))
+                rewind = (now_step - best_step) - sum(1 for st in skipped if best_step < st <= now_step)
+                best_saver.save_state(best_path, snap.checkpoint(best_step, rewind, meta, lr_at))
                 snap.written_step = best_step
         pending.clear()
 
@@ -907,6 +909,7 @@ def train_single_npz(npz_path: Path, out_dir: Path,
             # skips the batch; the step still counts so that schedules and checkpoints stay aligned with the reference
             schedulerD.step(); schedulerG.step()
             inst_noise = max(inst_noise_end, inst_noise - noise_decay)
+            skipped.append(step)
             continue
 
         if graphed is not None and x.shape[0] * _dist.world_size() == batch_size and inst_noise > 0:

@@ -152,6 +152,21 @@ def test_two_columns_per_thread_bptt_variant(B, T, I, H, L, dy_last):
         assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
 
 
+def test_cluster_capacity_is_reported():
+    """tg_cluster_capacity: resident-cluster capacity of the H = 128 / 256 kernels (cudaOccupancyMaxActiveClusters);
+    the launchers size the sequence groups per cluster from it so that one wave covers the batch."""
+    from timegan_b200._lib import lib
+    torch.zeros(1, device="cuda:0")
+    sms = lib.tg_device_sm_count()
+    for back in (0, 1, 2):
+        c = lib.tg_cluster_capacity(128, back, 1)
+        assert 1 <= c <= sms // 2, (back, c)
+    c8 = lib.tg_cluster_capacity(256, 0, 1)
+    assert 1 <= c8 <= sms // 8
+    assert lib.tg_cluster_capacity(256, 1, 3) >= 1           # the three-group BPTT instantiation fits (218 KB of smem)
+    assert lib.tg_cluster_capacity(64, 0, 1) == 0 and lib.tg_cluster_capacity(256, 2, 1) == 0
+
+
 def test_last_step_only_gradient():
     """Discriminator pattern (timegan_model.py:97): only y[:, -1] feeds the loss."""
     ops = _ops()

@@ -3,7 +3,7 @@
 # command, ncu --set full captures of the dominant kernels, config-5 inference.  Everything lands in gpurun_out/.
 set -u
 O=gpurun_out
-TAG=${1:-r01}
+TAG=${1:-r02}
 python -m pytest tests -m gpu -q 2>&1 | tail -4 > $O/${TAG}_pytest_gpu.log; cat $O/${TAG}_pytest_gpu.log | tail -2
 python -c "import __graft_entry__ as g; g.smoke()" > $O/${TAG}_smoke.log 2>&1; tail -1 $O/${TAG}_smoke.log
 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; echo "bench rc=$?"
@@ -17,4 +17,8 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:"gru
   python tools/prof_gru_once.py > $O/${TAG}_ncu_bwd.log 2>&1; echo "ncu bwd rc=$?"
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:"tc_gemm_tn_kernel" -s 3 -c 1 -o $O/${TAG}_prof_proj \
   python tools/prof_gru_once.py > $O/${TAG}_ncu_proj.log 2>&1; echo "ncu proj rc=$?"
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"gru_cl_bwd_kernel" -s 1 -c 1 -o $O/${TAG}_prof_gru_cl_bwd \
+  python tools/prof_cluster_once.py > $O/${TAG}_ncu_clbwd.log 2>&1; echo "ncu cluster bwd rc=$?"
+python tools/probe_cluster.py > $O/${TAG}_probe_cluster.log 2>&1; echo "probe cluster rc=$?"
+python tools/sweep_phases.py --hidden 24 64 128 256 --steps 6 > $O/${TAG}_sweep_phases_c4_1gpu.jsonl 2>/dev/null; echo "c4 rc=$?"
 python tools/bench_inference.py > $O/${TAG}_bench_inference_c5.json 2> $O/${TAG}_bench_inference_c5.err; echo "c5 rc=$?"; cat $O/${TAG}_bench_inference_c5.json | cut -c1-300
