@@ -65,6 +65,7 @@ class DeviceNoise:
         self.seed, self.device = int(seed) & 0x7FFFFFFFFFFFFFFF, device
         self.ctr = torch.zeros((), dtype=torch.int64, device=device)
         self.local = 0
+        self.held = False
 
     def _adv(self, n):
         o = self.local
@@ -72,12 +73,26 @@ class DeviceNoise:
         return o
 
     def begin(self):
-        self.local = 0
+        if not self.held:
+            self.local = 0
 
     def end(self):
+        if self.held:
+            return
         if self.local:
             self.ctr.add_(self.local)
         self.local = 0
+
+    def hold(self):
+        """Treat the step functions that follow as ONE transaction: their begin()/end() neither reset the offset nor
+        touch the device counter, so step functions running on different streams never race on it; release() advances
+        the counter once.  Every draw lands on the Philox position it has when the functions run one after another."""
+        self.local = 0
+        self.held = True
+
+    def release(self):
+        self.held = False
+        self.end()
 
     def rand(self, *shape):
         n = 1

@@ -143,6 +143,12 @@ class _DeviceNoiseAdapter:
     def end(self):
         self.src.end()
 
+    def hold(self):
+        self.src.hold()
+
+    def release(self):
+        self.src.release()
+
 
 _DEFAULT_NOISE: Dict[str, _DeviceNoiseAdapter] = {}
 
@@ -413,6 +419,15 @@ def set_concurrency(on: bool):
     _CONCURRENT = bool(on)
 
 
+# GraphedJointStep: let gen_step's D-independent forward passes overlap disc_step (TIMEGAN_B200_OVERLAP_STEPS=0: off)
+_OVERLAP_STEPS = os.environ.get("TIMEGAN_B200_OVERLAP_STEPS", "1") != "0"
+
+
+def set_step_overlap(on: bool):
+    global _OVERLAP_STEPS
+    _OVERLAP_STEPS = bool(on)
+
+
 class _Fork:
     """`with _Fork(device, k):` runs the block on side stream k after it has caught up with the current stream.
     The recurrent kernels are latency-bound (768 dependent steps per layer pass) and leave most of each SM idle,
@@ -587,8 +602,13 @@ def disc_step(model: TimeGAN, x, device, optD, label_smooth, inst_noise_std, cli
 
 def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_std, clip, schedulerG=None,
              gamma_cov: float = 0.0, gamma_acf: float = 0.0, acf_max_lag: int = 32, *, noise=None,
-             sync: bool = True):
-    """Generator/supervisor/embedder/recovery update (tt:228-276).  Returns the six logged losses."""
+             sync: bool = True, d_ready=None, fork_base: int = 0):
+    """Generator/supervisor/embedder/recovery update (tt:228-276).  Returns the six logged losses.
+
+    `d_ready` (a CUDA event) marks the point where the discriminator's weights are final: everything before the D
+    forward pass -- E -> R, G -> S -> R, the moment losses -- does not read them, so a caller that runs this function
+    on its own stream (GraphedJointStep) lets that part overlap the tail of disc_step and passes the event of D's
+    optimiser step here.  `fork_base`: first side-stream index this call may use."""
     model.generator.train(); model.supervisor.train(); model.embedder.train(); model.recovery.train()
     _dist.begin_step("G")
     nz = _noise_source(noise, device)
@@ -596,7 +616,7 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     B, T = x.size(0), x.size(1)
 
     z = nz.rand(B, T, model.embedder.rnn.rnn.hidden_size)                            # tt:235
-    fork_rec = _Fork(device, 0)
+    fork_rec = _Fork(device, fork_base)
     with fork_rec:                                   # E -> R on the real batch runs beside G -> S
         x_tilde = model.reconstruct(x)                                               # tt:247-248
         g_rec = recon_loss(x, x_tilde)
@@ -605,14 +625,16 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     d_in = add_instance_noise(h_hat, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:240 (noise drawn here)
     cov_term = torch.zeros((), device=device)
     acf_term = torch.zeros((), device=device)
-    fork_dec = _Fork(device, 1)
+    fork_dec = _Fork(device, fork_base + 1)
     with fork_dec:                                   # R on the generated latents runs beside D
         x_hat = model.decode(h_hat)                                                  # tt:251
         if gamma_cov > 0 or gamma_acf > 0:                                           # tt:254-263
             cov_term, acf_term = _losses.cov_acf_losses(x_hat, x, acf_max_lag, need_cov=gamma_cov > 0,
                                                         need_acf=gamma_acf > 0)
-    g_adv = model.discriminator.adv_loss(d_in)       # bce(D(d_in), ones) with D frozen: one head kernel (tt:240-241)
     g_sup = sup_loss_fake(h_hat)                                                     # tt:244
+    if d_ready is not None:
+        torch.cuda.current_stream(device).wait_event(d_ready)
+    g_adv = model.discriminator.adv_loss(d_in)       # bce(D(d_in), ones) with D frozen: one head kernel (tt:240-241)
     fork_rec.join()
     fork_dec.join()
     g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
@@ -667,10 +689,40 @@ class GraphedJointStep:
     def _joint(self):
         k = self.kw
         std = self.std if self._noise_on else 0.0
+        if not (_CONCURRENT and _OVERLAP_STEPS):
+            d = disc_step(self.model, self.x, self.device, self.optD, k["label_smooth"], std, k["clip"], None,
+                          k["r1_gamma"], target_acc=k["target_acc"], band=k["band"], noise=self.noise, sync=False)
+            g = gen_step(self.model, self.x, self.device, self.optG, k["alpha_sup"], k["beta_rec"], std, k["clip"],
+                         None, k["gamma_cov"], k["gamma_acf"], k["acf_max_lag"], noise=self.noise, sync=False)
+            return torch.stack([v.float().reshape(()) for v in tuple(d) + tuple(g)])
+        # gen_step reads the discriminator only from its D forward pass on (tt:240); E, G, S, R are not touched by
+        # disc_step's optimiser.  So gen_step runs on its own stream that depends on the START of the joint step and
+        # waits for D's update right before it needs D: its E -> R / G -> S -> R forward passes (15 of the step's 54
+        # layer passes) fill the SMs beside disc_step's R1 chain.  Issue order, noise positions and all-reduce call
+        # sites are those of the sequential step; only the dependencies the CUDA graph records differ.
+        main = torch.cuda.current_stream(self.device)
+        pool = _SIDE_STREAMS.setdefault(str(self.device), [])
+        while len(pool) <= 4:
+            pool.append(torch.cuda.Stream(device=self.device))
+        gstream = pool[4]
+        nz = _noise_source(self.noise, self.device)
+        hold = hasattr(nz, "hold")
+        if hold:
+            nz.hold()
+        start = torch.cuda.Event()
+        start.record(main)
         d = disc_step(self.model, self.x, self.device, self.optD, k["label_smooth"], std, k["clip"], None,
                       k["r1_gamma"], target_acc=k["target_acc"], band=k["band"], noise=self.noise, sync=False)
-        g = gen_step(self.model, self.x, self.device, self.optG, k["alpha_sup"], k["beta_rec"], std, k["clip"], None,
-                     k["gamma_cov"], k["gamma_acf"], k["acf_max_lag"], noise=self.noise, sync=False)
+        d_ready = torch.cuda.Event()
+        d_ready.record(main)
+        gstream.wait_event(start)
+        with torch.cuda.stream(gstream):
+            g = gen_step(self.model, self.x, self.device, self.optG, k["alpha_sup"], k["beta_rec"], std, k["clip"],
+                         None, k["gamma_cov"], k["gamma_acf"], k["acf_max_lag"], noise=self.noise, sync=False,
+                         d_ready=d_ready, fork_base=2)
+        main.wait_stream(gstream)
+        if hold:
+            nz.release()
         return torch.stack([v.float().reshape(()) for v in tuple(d) + tuple(g)])
 
     def __call__(self, x, inst_noise_std: float):
