@@ -70,7 +70,7 @@ def parse():
     ap.add_argument("--hidden", type=int, default=64)
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--batch", type=int, default=256, help="sequences per GPU")
-    ap.add_argument("--proj", type=str, default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--proj", type=str, default="fp32", choices=["fp32", "bf16", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-also-c3", dest="also_c3", action="store_false",
                     help="skip the secondary BASELINE config c3 (h=128, reduced-precision projections) line under `also`")
@@ -85,7 +85,9 @@ def parse():
 
 
 PROJ_LABEL = {"fp32": "fp32 (3xTF32) projections",
-              "bf16": "reduced-precision projections (one TF32 pass over fp32 operands; BASELINE's 'bf16 input projections' slot)"}
+              "bf16": "bf16 input projections (bf16 operands on tcgen05 kind::f16, bf16 gi read by the recurrence; dX and "
+                      "weight gradients one TF32 pass)",
+              "tf32": "reduced-precision projections (one TF32 pass over fp32 operands)"}
 
 
 def workload_name(a):
@@ -492,7 +494,8 @@ def run_ours(a):
     line = {
         "metric": METRIC, "value": round(seqs / (ms * 1e-3), 2), "unit": "seq/s", "n_gpus": world, "steps": a.steps,
         "warmup": max(a.warmup, 3), "ms_per_step": round(ms / a.steps, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "fp32" if a.proj == "fp32" else "fp32 (tf32 projections)",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "fp32", "tf32": "fp32 (tf32 projections)",
+                                                       "bf16": "fp32 recurrence, bf16 input projections"}[a.proj],
         "data": "synthetic",
         "config": bench_config(a, world),
         "e2e": {"value": round(seqs / (ms_e2e * 1e-3), 2), "unit": "seq/s",

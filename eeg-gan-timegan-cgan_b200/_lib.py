@@ -14,7 +14,7 @@ LIB_PATH = _PKG / "libtimegan_b200.so"
 
 # flags (keep in sync with include/timegan_b200.h)
 GRU_SAVE, GRU_NO_BULK, GRU_DY_LAST = 1, 2, 4
-PROJ_FP32, PROJ_BF16, PROJ_TF32X3 = 0, 1, 2
+PROJ_FP32, PROJ_TF32, PROJ_TF32X3 = 0, 1, 2
 
 if not LIB_PATH.exists():
     raise ImportError(
@@ -40,12 +40,15 @@ SIGNATURES = {
     "tg_prof_reset": (None, []),
     "tg_prof_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tg_proj": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i]),
+    "tg_bf16_gi_supported": (_i, [_i, _i, _i]),
+    "tg_proj_bf16": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i]),
     "tg_dgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i]),
     "tg_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),
     "tg_wgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _sz, _i]),
     "tg_wgrad_gru_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "tg_wgrad_gru": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _i]),
     "tg_gru_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
+    "tg_gru_fwd_bf16gi": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "tg_gru_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "tg_gru_jvp_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "tg_gru_jvp_bwd": (_i, [_vp] * 14 + [_i, _i, _i, _i, _vp]),

@@ -219,12 +219,22 @@ int tg_prof_read(int kind, double* ms, long long* calls, double* bytes, double* 
 int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
             int M, int N, int K, int accumulate, int mode) {
   ProfScope _ps(stream, K_PROJ, 4.0 * ((double)M * K + (double)N * K + (double)M * N), 2.0 * M * N * K);
-  if (mode == TG_PROJ_BF16 || mode == TG_PROJ_TF32X3) {
+  if (mode == TG_PROJ_TF32 || mode == TG_PROJ_TF32X3) {
     int rc = tg_proj_tc_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate,
                              mode == TG_PROJ_TF32X3 ? 3 : 1);
     if (rc != TG_ERR_UNSUPPORTED) return rc;  // shapes the tensor-core tile cannot take run on the FFMA path
   }
   return tg_gemm_nt_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
+}
+
+int tg_bf16_gi_supported(int M, int K, int H) {
+  return (tg_gru_fwd_bf16gi_ok(H) && M >= 128 && K % 4 == 0 && K <= 512) ? 1 : 0;
+}
+
+int tg_proj_bf16(void* stream, const float* A, int lda, const void* W16, int ldw, const float* bias, void* C16, int ldc,
+                 int M, int N, int K) {
+  ProfScope _ps(stream, K_PROJ, 4.0 * (double)M * K + 2.0 * (double)N * K + 2.0 * (double)M * N, 2.0 * M * N * K);
+  return tg_proj_bf16_impl((cudaStream_t)stream, A, lda, W16, ldw, bias, C16, ldc, M, N, K);
 }
 
 int tg_dgrad(void* stream, const float* dG, int ldg, const float* W, int ldw, float* dX, int ldx, int M, int N, int K,
@@ -241,7 +251,7 @@ size_t tg_wgrad_workspace_bytes(int M, int N, int K) {
 int tg_wgrad(void* stream, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw, float* db, int M,
              int N, int K, int a_shift_T, int accumulate, void* ws, size_t ws_bytes, int mode) {
   ProfScope _ps(stream, K_WGRAD, 4.0 * ((double)M * N + (double)M * K + (double)N * K), 2.0 * M * N * K);
-  if (mode == TG_PROJ_BF16 || mode == TG_PROJ_TF32X3) {
+  if (mode == TG_PROJ_TF32 || mode == TG_PROJ_TF32X3) {
     int rc = tg_wgrad_tc_impl((cudaStream_t)stream, dG, ldg, A, lda, dW, lddw, db, M, N, K, a_shift_T, accumulate,
                               (float*)ws, ws_bytes, mode == TG_PROJ_TF32X3 ? 3 : 1);
     if (rc != TG_ERR_UNSUPPORTED) return rc;
@@ -265,7 +275,7 @@ int tg_wgrad_gru(void* stream, const float* dgi, const float* dq, const float* x
                  float* dW_hh, float* db_ih, float* db_hh, int B, int T, int I, int H, int accumulate, void* ws,
                  size_t ws_bytes, int mode) {
   const int M = B * T;
-  if (mode == TG_PROJ_BF16 || mode == TG_PROJ_TF32X3) {
+  if (mode == TG_PROJ_TF32 || mode == TG_PROJ_TF32X3) {
     ProfScope _ps(stream, K_WGRAD, 4.0 * M * (4.0 * H + (x ? I : 0) + H), 2.0 * M * 3.0 * H * ((x ? I : 0) + H));
     int rc = tg_wgrad_gru_tc_impl((cudaStream_t)stream, dgi, dq, x, ldx, y, dW_ih, dW_hh, db_ih, db_hh, B, T, I, H,
                                   accumulate, (float*)ws, ws_bytes, mode == TG_PROJ_TF32X3 ? 3 : 1);
@@ -287,6 +297,12 @@ int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, fl
                int flags) {
   ProfScope _ps(stream, K_GRU_FWD, (double)B * T * H * ((flags & TG_GRU_SAVE) ? 32.0 : 16.0), 6.0 * B * T * (double)H * H);
   return tg_gru_fwd_impl((cudaStream_t)stream, gi, w_hh, b_hh, y, q, B, T, H, flags);
+}
+
+int tg_gru_fwd_bf16gi(void* stream, const void* gi16, const float* w_hh, const float* b_hh, float* y, float* q,
+                      float* rzn, int B, int T, int H, int flags) {
+  ProfScope _ps(stream, K_GRU_FWD, (double)B * T * H * ((flags & TG_GRU_SAVE) ? 26.0 : 10.0), 6.0 * B * T * (double)H * H);
+  return tg_gru_fwd_bf16gi_impl((cudaStream_t)stream, gi16, w_hh, b_hh, y, q, rzn, B, T, H, flags);
 }
 
 int tg_gru_bwd(void* stream, const float* dy, const float* rzn, const float* q, const float* y, const float* w_hh,

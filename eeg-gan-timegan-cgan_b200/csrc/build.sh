@@ -6,7 +6,7 @@ OUT="$HERE/../libtimegan_b200.so"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-Wall -Xptxas -v
        --expt-relaxed-constexpr -I"$HERE" -I"$HERE/../../include")
-SRCS=(api gru_fwd gru_bwd gru_jvp gru_bigh gru_cluster gemm_ffma proj_tcgen05 wgrad_tcgen05 wgrad_gru_tcgen05 losses optim rng peer_allreduce eval_stats head)
+SRCS=(api proj_bf16 gru_fwd gru_bwd gru_jvp gru_bigh gru_cluster gemm_ffma proj_tcgen05 wgrad_tcgen05 wgrad_gru_tcgen05 losses optim rng peer_allreduce eval_stats head)
 mkdir -p "$HERE/build"
 pids=()
 for s in "${SRCS[@]}"; do

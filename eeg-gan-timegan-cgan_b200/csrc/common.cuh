@@ -130,6 +130,12 @@ __device__ __forceinline__ float lds_f32(uint32_t a) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
   return v;
 }
+// one bf16 value from shared memory, widened to fp32 (exact)
+__device__ __forceinline__ float lds_bf16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+  return __uint_as_float((uint32_t)v << 16);
+}
 __device__ __forceinline__ float4 lds_v4(uint32_t a) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));

@@ -28,6 +28,9 @@ struct FwdParams {
   int B, T, H;
   int save;
   int bulk;
+  // bf16-gi mode (GIB instantiations): gi16 (B,T,3H) bf16 is read-only, r,z,n go to their own fp32 tensor
+  const unsigned short* gi16;
+  float* rzn;
 };
 
 constexpr int HS_PAD = 16;  // h rows are HP+16 floats apart: the two sequences a lane pair writes hit different banks
@@ -37,7 +40,9 @@ constexpr int fwd_min_blocks() { return (HP * G <= 128) ? 3 : ((HP * G <= 256) ?
 
 // EXACT: H == HP is a compile-time fact (c2: 64, c3: 128) -- every stride in the hot loop becomes an immediate and
 // the "is this hidden unit real" predicate disappears.
-template <int HP, int G, int BT, int TC, int NST, bool EXACT>
+// GIB: the input projection arrives as bf16 (proj_bf16.cu) -- 6H instead of 12H bytes per cell on the way in; the saved
+// r,z,n stay fp32 (BPTT reads them unchanged) and therefore get their own stream instead of overwriting gi.
+template <int HP, int G, int BT, int TC, int NST, bool EXACT, bool GIB = false>
 __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() == 1) ? fwd_min_blocks<HP, G, BT>() : fwd_min_blocks<HP, G, BT>() - 1) gru_fwd_kernel(FwdParams p) {
   constexpr int KS = HP / G;                     // k values per lane
   constexpr int NOWN = (BT >= G) ? BT / G : 1;   // sequences a lane finishes per step
@@ -59,8 +64,15 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
   uint64_t* bars = reinterpret_cast<uint64_t*>(hs + 2 * BT * HR);  // [NST]
   float* stages = reinterpret_cast<float*>(smem_raw + ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128);
 
-  ChunkPipe<3, BT, TC, NST> pipe;
-  pipe.g[0] = pipe.gst[0] = p.gi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | (p.save ? TG_STRM_STORE : 0); pipe.shift[0] = 0;
+  ChunkPipe<GIB ? 4 : 3, BT, TC, NST> pipe;
+  if constexpr (GIB) {
+    // stream 0: 3H bf16 = 3H/2 floats per row, load only; stream 3: r,z,n fp32, store only
+    pipe.g[0] = pipe.gst[0] = reinterpret_cast<float*>(const_cast<unsigned short*>(p.gi16));
+    pipe.w[0] = 3 * H / 2; pipe.mode[0] = TG_STRM_LOAD; pipe.shift[0] = 0;
+    pipe.g[3] = pipe.gst[3] = p.rzn; pipe.w[3] = 3 * H; pipe.mode[3] = p.save ? TG_STRM_STORE : 0; pipe.shift[3] = 0;
+  } else {
+    pipe.g[0] = pipe.gst[0] = p.gi; pipe.w[0] = 3 * H; pipe.mode[0] = TG_STRM_LOAD | (p.save ? TG_STRM_STORE : 0); pipe.shift[0] = 0;
+  }
   pipe.g[1] = pipe.gst[1] = p.q;  pipe.w[1] = H;     pipe.mode[1] = p.save ? TG_STRM_STORE : 0;                  pipe.shift[1] = 0;
   pipe.g[2] = pipe.gst[2] = p.y;  pipe.w[2] = H;     pipe.mode[2] = TG_STRM_STORE;                               pipe.shift[2] = 0;
   pipe.layout();
@@ -103,7 +115,8 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
     // one sequence per CTA and H == HP: every lane is live -- a compile-time fact, so the stores need no branch
     act[o] = (EXACT && BT == 1) || ((EXACT || j < H) && (ob[o] < nb));
   }
-  const uint32_t gi_step = 12u * (uint32_t)H, h_step = 4u * (uint32_t)H;
+  const uint32_t gi_step = (GIB ? 6u : 12u) * (uint32_t)H, h_step = 4u * (uint32_t)H;
+  const uint32_t gate_step = GIB ? 2u * (uint32_t)H : h_step;     // bytes between the r, z, n blocks of an input row
   const uint32_t lane_k = 16u * (uint32_t)ql;          // this lane's first float4 of h
   const bool save = p.save != 0;
   // the lane that owns sequence b seeds b's accumulators with the hidden biases of the r and z gates: the
@@ -118,6 +131,7 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
 
   int cur = 0;
   uint32_t a_gi[NOWN], a_q[NOWN], a_y[NOWN];
+  uint32_t a_rz[GIB ? NOWN : 1];       // GIB: where r,z,n are staged (their own stream); otherwise they overwrite gi
 
   // One timestep.  Everything is computed unconditionally (inactive lanes work on row 0 of the stage and never
   // store), so the body is branch-free: the warps do not pay for BSSY/BSYNC reconvergence every step.
@@ -128,7 +142,11 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
     float gr[NOWN], gz[NOWN], gn[NOWN];
 #pragma unroll
     for (int o = 0; o < NOWN; ++o) {
-      gr[o] = lds_f32(a_gi[o]); gz[o] = lds_f32(a_gi[o] + h_step); gn[o] = lds_f32(a_gi[o] + 2u * h_step);
+      if constexpr (GIB) {
+        gr[o] = lds_bf16(a_gi[o]); gz[o] = lds_bf16(a_gi[o] + gate_step); gn[o] = lds_bf16(a_gi[o] + 2u * gate_step);
+      } else {
+        gr[o] = lds_f32(a_gi[o]); gz[o] = lds_f32(a_gi[o] + h_step); gn[o] = lds_f32(a_gi[o] + 2u * h_step);
+      }
     }
     // two accumulator pairs per (sequence, gate): six independent FFMA2 chains per sequence keep the FMA pipe
     // issuing every other cycle instead of waiting out the FFMA2 latency
@@ -206,16 +224,18 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
       const float r = sigmoid_mufu(gr[o] + own[o][0]);
       const float z = sigmoid_mufu(gz[o] + own[o][1]);
       const float qv = own[o][2] + bh[2];
-      if (save && act[o]) { sts_f32(a_gi[o], r); sts_f32(a_gi[o] + h_step, z); sts_f32(a_q[o], qv); }
+      const uint32_t a_s = GIB ? a_rz[GIB ? o : 0] : a_gi[o];
+      if (save && act[o]) { sts_f32(a_s, r); sts_f32(a_s + h_step, z); sts_f32(a_q[o], qv); }
       const float n = tanh_mufu(fmaf(r, qv, gn[o]));
       const float h = fmaf(z, hprev[o] - n, n);
       hprev[o] = h;
       if (act[o]) {
         sts_f32(hn + (uint32_t)(ob[o] * HR + j) * 4u, h);
         sts_f32(a_y[o], h);
-        if (save) sts_f32(a_gi[o] + 2u * h_step, n);
+        if (save) sts_f32(a_s + 2u * h_step, n);
       }
       a_gi[o] += gi_step; a_q[o] += h_step; a_y[o] += h_step;
+      if constexpr (GIB) a_rz[o] += 3u * h_step;
     }
     cur ^= 1;
   };
@@ -228,7 +248,8 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
     for (int o = 0; o < NOWN; ++o) {
       const int b = act[o] ? ob[o] : 0;
       const int jj = act[o] ? j : 0;
-      a_gi[o] = pipe.row_addr(s, 0, b, 0) + 4u * (uint32_t)jj;
+      a_gi[o] = pipe.row_addr(s, 0, b, 0) + (GIB ? 2u : 4u) * (uint32_t)jj;
+      if constexpr (GIB) a_rz[o] = pipe.row_addr(s, 3, b, 0) + 4u * (uint32_t)jj;
       a_q[o] = pipe.row_addr(s, 1, b, 0) + 4u * (uint32_t)jj;
       a_y[o] = pipe.row_addr(s, 2, b, 0) + 4u * (uint32_t)jj;
     }
@@ -243,6 +264,20 @@ __global__ void __launch_bounds__(HP* G, (EXACT || fwd_min_blocks<HP, G, BT>() =
     pipe.release(c);
   }
   pipe.drain();
+}
+
+// bf16-gi launcher (H == HP only: c2's 64 and c3's 128)
+template <int HP, int G, int BT, int TC, int NST>
+int launch_fwd_gib(cudaStream_t st, const FwdParams& p) {
+  constexpr int HR = HP + HS_PAD;
+  const int widths[4] = {3 * p.H / 2, p.H, p.H, 3 * p.H};
+  size_t smem = ((2 * BT * HR * 4 + NST * 8 + 127) / 128) * 128 +
+                (size_t)NST * ChunkPipe<4, BT, TC, NST>::stage_floats_for(widths) * 4;
+  TG_OPT_IN_SMEM((gru_fwd_kernel<HP, G, BT, TC, NST, true, true>), "gru_fwd(bf16 gi)");
+  if (smem > (size_t)tg_max_optin_smem()) { tg_set_error("gru_fwd(bf16 gi): needs %zu B of shared memory", smem); return TG_ERR_UNSUPPORTED; }
+  dim3 grid((p.B + BT - 1) / BT), block(HP * G);
+  gru_fwd_kernel<HP, G, BT, TC, NST, true, true><<<grid, block, smem, st>>>(p);
+  return tg_check_launch("gru_fwd(bf16 gi)");
 }
 
 template <int HP, int G, int BT, int TC, int NST>
@@ -276,6 +311,19 @@ int dispatch_bt(cudaStream_t st, const FwdParams& p, int bt) {
   return TG_ERR_ARG;
 }
 
+template <int HP, int G>
+int dispatch_bt_gib(cudaStream_t st, const FwdParams& p, int bt) {
+  constexpr int NST = 3;
+  // the separate r,z,n stream makes a stage 6.5H floats per sequence-step (in place: 5H)
+  switch (bt) {
+    case 1: return launch_fwd_gib<HP, G, 1, (HP <= 64) ? 16 : 8, NST>(st, p);
+    case 2: return launch_fwd_gib<HP, G, 2, 8, NST>(st, p);
+    case 4: return launch_fwd_gib<HP, G, 4, (HP <= 64) ? 8 : 4, NST>(st, p);
+  }
+  tg_set_error("gru_fwd(bf16 gi): bad BT %d", bt);
+  return TG_ERR_ARG;
+}
+
 }  // namespace
 
 // Sequences per CTA.  The recurrent kernels are bound by the per-step dependency chain (about 550 clk even with
@@ -300,11 +348,30 @@ int tg_gru_fwd_impl(cudaStream_t st, float* gi, const float* whh, const float* b
       (!save || tg_aligned16(q)))
     return tg_gru_cl_fwd(st, gi, whh, bhh, y, q, B, T, H, save);
   if (H > 128) return tg_bigh_fwd(st, gi, whh, bhh, y, q, B, T, H, save);
-  FwdParams p{gi, whh, bhh, y, q, B, T, H, save, 0};
+  FwdParams p{gi, whh, bhh, y, q, B, T, H, save, 0, nullptr, nullptr};
   p.bulk = (H % 4 == 0) && tg_aligned16(gi) && tg_aligned16(y) && (!save || tg_aligned16(q)) &&
            !(flags & TG_GRU_NO_BULK);
   const int bto = (flags >> 8) & 0xff;
   if (H <= 32) return dispatch_bt<32, 2>(st, p, tg_pick_bt(B, 32, bto));
   if (H <= 64) return dispatch_bt<64, 2>(st, p, tg_pick_bt(B, 64, bto));
   return dispatch_bt<128, 4>(st, p, tg_pick_bt(B, 128, bto));
+}
+
+bool tg_gru_fwd_bf16gi_ok(int H) { return H == 64 || H == 128; }
+
+// forward pass fed by the bf16 projection (proj_bf16.cu): gi16 (B,T,3H) bf16 in; y, and with TG_GRU_SAVE rzn (B,T,3H)
+// fp32 and q out
+int tg_gru_fwd_bf16gi_impl(cudaStream_t st, const void* gi16, const float* whh, const float* bhh, float* y, float* q,
+                           float* rzn, int B, int T, int H, int flags) {
+  TG_REQUIRE(gi16 && whh && bhh && y, TG_ERR_ARG, "gru_fwd(bf16 gi): null pointer");
+  TG_REQUIRE(B > 0 && T > 0, TG_ERR_SHAPE, "gru_fwd(bf16 gi): bad shape B=%d T=%d", B, T);
+  if (!tg_gru_fwd_bf16gi_ok(H)) { tg_set_error("gru_fwd(bf16 gi): hidden size %d not instantiated (64, 128)", H); return TG_ERR_UNSUPPORTED; }
+  const int save = (flags & TG_GRU_SAVE) ? 1 : 0;
+  TG_REQUIRE(!save || (q && rzn), TG_ERR_ARG, "gru_fwd(bf16 gi): save requested without q / rzn buffers");
+  TG_REQUIRE(tg_aligned16(gi16) && tg_aligned16(y) && (!save || (tg_aligned16(q) && tg_aligned16(rzn))), TG_ERR_ALIGN,
+             "gru_fwd(bf16 gi): buffers must be 16-byte aligned");
+  FwdParams p{nullptr, whh, bhh, y, q, B, T, H, save, 1, reinterpret_cast<const unsigned short*>(gi16), rzn};
+  const int bto = (flags >> 8) & 0xff;
+  if (H == 64) return dispatch_bt_gib<64, 2>(st, p, tg_pick_bt(B, 64, bto));
+  return dispatch_bt_gib<128, 4>(st, p, tg_pick_bt(B, 128, bto));
 }

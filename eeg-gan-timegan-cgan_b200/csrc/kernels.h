@@ -61,6 +61,14 @@ size_t tg_wgrad_ws_bytes(int M, int N, int K);
 int tg_proj_tc_impl(cudaStream_t st, const float* A, int lda, const float* W, int ldw, const float* bias, float* C,
                     int ldc, int M, int N, int K, int accumulate, int passes);
 
+// bf16 input projection (proj_bf16.cu): fp32 A converted in shared memory, bf16 W, bf16 result; and the forward
+// recurrence that reads it (gru_fwd.cu, H = 64 / 128)
+int tg_proj_bf16_impl(cudaStream_t st, const float* A, int lda, const void* W16, int ldw, const float* bias, void* C16,
+                      int ldc, int M, int N, int K);
+bool tg_gru_fwd_bf16gi_ok(int H);
+int tg_gru_fwd_bf16gi_impl(cudaStream_t st, const void* gi16, const float* whh, const float* bhh, float* y, float* q,
+                           float* rzn, int B, int T, int H, int flags);
+
 // tensor-core weight gradient (tcgen05, MN-major operands); TG_ERR_UNSUPPORTED for shapes it cannot take
 size_t tg_wgrad_tc_ws_bytes(int M, int N, int K);
 int tg_wgrad_tc_impl(cudaStream_t st, const float* dG, int ldg, const float* A, int lda, float* dW, int lddw,

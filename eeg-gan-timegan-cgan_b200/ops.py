@@ -22,9 +22,13 @@ _PROJ_MODE = _lib.PROJ_TF32X3
 _BT_OVERRIDE = 0  # sequences per CTA override for the recurrent kernels (0 = heuristic)
 
 
-_MODES = {"ffma": _lib.PROJ_FP32, "fp32": _lib.PROJ_TF32X3, "bf16": _lib.PROJ_BF16, "tf32": _lib.PROJ_BF16,
+_MODES = {"ffma": _lib.PROJ_FP32, "fp32": _lib.PROJ_TF32X3, "bf16": _lib.PROJ_TF32, "tf32": _lib.PROJ_TF32,
           "tf32x3": _lib.PROJ_TF32X3}
 _MODE_NAME = "fp32"
+# "bf16" mode: the GRU input projections X W_ih^T run with bf16 operands (tcgen05 kind::f16) and store a bf16 result that
+# the forward recurrence reads directly (tg_proj_bf16 / tg_gru_fwd_bf16gi); every other contraction of the step (dX,
+# weight gradients) takes one TF32 pass, the heads and the R1 tangent projections stay in fp32-parity precision.
+_BF16_GI = False
 
 
 def set_proj_mode(mode: str):
@@ -32,11 +36,13 @@ def set_proj_mode(mode: str):
     "ffma"   exact fp32 on CUDA cores;
     "tf32x3" tcgen05 tensor cores, 3xTF32 split (fp32-parity mode, 1e-4);
     "fp32"   alias of the fp32-parity mode in use (see _MODES);
-    "bf16" / "tf32"  tcgen05 tensor cores, one TF32 pass (reduced-precision projection mode, 2e-2)."""
-    global _PROJ_MODE, _MODE_NAME
+    "tf32"   tcgen05 tensor cores, one TF32 pass over the fp32 operands (reduced precision, 2e-2);
+    "bf16"   BASELINE config c3's "bf16 input projections": bf16 operands and a bf16 gi tensor for the input
+             projections (layers with H = 64 / 128; others fall back to "tf32"), one TF32 pass elsewhere (2e-2)."""
+    global _PROJ_MODE, _MODE_NAME, _BF16_GI
     if mode not in _MODES:
         raise ValueError(f"proj mode must be one of {sorted(_MODES)}")
-    _PROJ_MODE, _MODE_NAME = _MODES[mode], mode
+    _PROJ_MODE, _MODE_NAME, _BF16_GI = _MODES[mode], mode, mode == "bf16"
 
 
 def get_proj_mode() -> str:
@@ -247,16 +253,29 @@ def stack_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], save: bool,
     for l in range(L):
         w_ih, w_hh, b_ih, b_hh = _layer_weights(weights, l)
         H = w_hh.shape[1]
-        gi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=x.device)
         ipad = 0
         if inp.shape[-1] % 4 != 0 and _PROJ_MODE != _lib.PROJ_FP32 and B * T >= 128:
             inp, ipad = pad_cols(inp)               # (B,T,14) -> (B,T,16): layer 0 of the embedder
             w_ih, _ = pad_cols(w_ih)
-        proj(inp.view(B * T, -1), w_ih, b_ih, gi.view(B * T, 3 * H))
         y = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
         q = torch.empty(B, T, H, dtype=torch.float32, device=x.device) if save else None
-        check(lib.tg_gru_fwd(stream_ptr(), ptr(gi), ptr(w_hh), ptr(b_hh), ptr(y), ptr(q), B, T, H,
-                             _flags(_lib.GRU_SAVE if save else 0)), "tg_gru_fwd")
+        K = inp.shape[-1]
+        if _BF16_GI and lib.tg_bf16_gi_supported(B * T, K, H):
+            # bf16 input projection: bf16 operands, bf16 gi (half the bytes of the layer's largest tensor, out of the
+            # projection and into the recurrence); r,z,n are saved in fp32 in their own tensor
+            gi16 = torch.empty(B, T, 3 * H, dtype=torch.bfloat16, device=x.device)
+            w16 = w_ih.to(torch.bfloat16)
+            a2 = inp.view(B * T, K)
+            check(lib.tg_proj_bf16(stream_ptr(), ptr(a2), a2.stride(0), ptr(w16), w16.stride(0), ptr(b_ih), ptr(gi16),
+                                   3 * H, B * T, 3 * H, K), "tg_proj_bf16")
+            gi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=x.device) if save else None
+            check(lib.tg_gru_fwd_bf16gi(stream_ptr(), ptr(gi16), ptr(w_hh), ptr(b_hh), ptr(y), ptr(q), ptr(gi), B, T, H,
+                                        _flags(_lib.GRU_SAVE if save else 0)), "tg_gru_fwd_bf16gi")
+        else:
+            gi = torch.empty(B, T, 3 * H, dtype=torch.float32, device=x.device)
+            proj(inp.view(B * T, -1), w_ih, b_ih, gi.view(B * T, 3 * H))
+            check(lib.tg_gru_fwd(stream_ptr(), ptr(gi), ptr(w_hh), ptr(b_hh), ptr(y), ptr(q), B, T, H,
+                                 _flags(_lib.GRU_SAVE if save else 0)), "tg_gru_fwd")
         if save:
             saves.append(LayerSave(inp, gi, q, y, ipad))
         inp = y
@@ -348,7 +367,7 @@ def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Seque
         H = w_hh.shape[1]
         gid = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
         proj(tin.view(B * T, -1), w_ih, None, gid.view(B * T, 3 * H),
-             mode=_lib.PROJ_FP32 if _PROJ_MODE == _lib.PROJ_BF16 else _PROJ_MODE)
+             mode=_lib.PROJ_FP32 if _PROJ_MODE == _lib.PROJ_TF32 else _PROJ_MODE)
         ydot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         qdot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         check(lib.tg_gru_jvp_fwd(stream_ptr(), ptr(gid), ptr(sv.rzn), ptr(sv.q), ptr(sv.y), ptr(w_hh), ptr(ydot),

@@ -38,8 +38,7 @@ extern "C" {
 
 /* projection precision */
 #define TG_PROJ_FP32 0   /* CUDA-core FFMA, exact fp32 */
-#define TG_PROJ_BF16 1   /* tcgen05 tensor cores, one TF32 pass over the fp32 operands (reduced-precision projection
-                            mode, bound 2e-2; TF32 keeps 10 mantissa bits vs bf16's 7 and needs no conversion pass) */
+#define TG_PROJ_TF32 1   /* tcgen05 tensor cores, one TF32 pass over the fp32 operands (reduced precision, bound 2e-2) */
 #define TG_PROJ_TF32X3 2 /* tcgen05 tensor cores, 3xTF32 split (hi*hi + hi*lo + lo*hi): fp32-parity mode, 1e-4 */
 
 int tg_version(void);
@@ -68,9 +67,18 @@ int tg_prof_read(int kind, double* ms, long long* calls, double* bytes, double* 
 /* ---- GRU layer, time-batched input projection:  C[M,N] (+)= A[M,K] W[N,K]^T + bias[N] -------------------
  * Replaces `params.linear_ih(input)` inside at::gru reached from timegan_model.py:33 (GRUStack.forward),
  * and the head Linears timegan_model.py:53 (Recovery.out), :66 (Generator.proj), :79 (Supervisor.proj).
- * bias may be NULL.  mode: TG_PROJ_FP32 | TG_PROJ_BF16. */
+ * bias may be NULL.  mode: TG_PROJ_FP32 | TG_PROJ_TF32 | TG_PROJ_TF32X3. */
 int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc,
             int M, int N, int K, int accumulate, int mode);
+
+/* ---- the "bf16 input projection" mode (BASELINE config c3): C16[M,N] = bf16(A) bf16(W16)^T + bias as bf16 -----------
+ * A (M,K) fp32 is converted to bf16 inside the kernel (no bf16 copy of an activation is written to memory), W16 (N,K) is
+ * bf16, the MMA is tcgen05 kind::f16 with fp32 accumulation, the result C16 (M,N) is bf16: 2 bytes per gate
+ * pre-activation out of the projection and into tg_gru_fwd_bf16gi.  lda in floats, ldw / ldc in bf16 elements.
+ * tg_bf16_gi_supported: 1 when both kernels take this layer (M = B*T rows, K inputs, hidden size H: H = 64 or 128). */
+int tg_bf16_gi_supported(int M, int K, int H);
+int tg_proj_bf16(void* stream, const float* A, int lda, const void* W16, int ldw, const float* bias, void* C16, int ldc,
+                 int M, int N, int K);
 
 /* ---- dX[M,N] (+)= dG[M,K] W[K,N]  (autograd of the projection w.r.t. its input; loss.backward() at
  * train_timegan.py:140,159,219,267) */
@@ -100,6 +108,11 @@ int tg_wgrad_gru(void* stream, const float* dgi, const float* dq, const float* x
  * h_{t-1} W_hn^T + b_hn.  y (B,T,H) receives h_t.  h0 = 0 (the reference never passes an initial state). */
 int tg_gru_fwd(void* stream, float* gi, const float* w_hh, const float* b_hh, float* y, float* q, int B, int T, int H,
                int flags);
+
+/* Same recurrence fed by tg_proj_bf16: gi16 (B,T,3H) bf16 is read-only (6H instead of 12H bytes per cell); with
+ * TG_GRU_SAVE r,z,n go to rzn (B,T,3H) fp32 and q as above, so BPTT and the R1 passes read what they always read. */
+int tg_gru_fwd_bf16gi(void* stream, const void* gi16, const float* w_hh, const float* b_hh, float* y, float* q,
+                      float* rzn, int B, int T, int H, int flags);
 
 /* ---- persistent BPTT of one layer (autograd of the nn.GRU loop; train_timegan.py:140,159,219,267,200) -----
  * in: dy (B,T,H) [or (B,H) with TG_GRU_DY_LAST], saved rzn,q, layer output y.  out: dgi (B,T,3H) =

@@ -114,3 +114,30 @@ def test_wgrad_tensor_core_modes(M, N, K, T, mode, tol):
     ops.wgrad(dGd, A.to(DEV), dW, None, N, shift_T=T, accumulate=True, mode=ops._MODES[mode])
     assert relerr(dW, 2 * ref_w) < tol
     assert relerr(db, ref_b) < 1e-5      # untouched when db is not requested
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 64), (1061, 384, 128), (777, 192, 16), (4096, 384, 64), (128, 192, 128),
+                                   (196608, 192, 64), (113664, 384, 128)])
+def test_proj_bf16_operands_and_bf16_result(M, N, K):
+    """tg_proj_bf16 (the 'bf16 input projections' of BASELINE config c3): fp32 activations converted to bf16 inside the
+    kernel, bf16 W, fp32 accumulation, bf16 result.  Against the same contraction of the bf16-ROUNDED operands in fp64,
+    rounded to bf16: at most one bf16 ulp apart (accumulation order), i.e. <= 2^-7 relative per element."""
+    from timegan_b200._lib import lib, check, ptr, stream_ptr
+    g = torch.Generator().manual_seed(M + K)
+    A = torch.rand(M, K, generator=g) * 2 - 0.7
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    Ad, bd = A.to(DEV), b.to(DEV)
+    W16 = W.to(DEV).to(torch.bfloat16)
+    C16 = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=DEV)
+    check(lib.tg_proj_bf16(stream_ptr(), ptr(Ad), K, ptr(W16), K, ptr(bd), ptr(C16), N, M, N, K), "tg_proj_bf16")
+    ref = A.to(torch.bfloat16).double() @ W.to(torch.bfloat16).double().T + b.double()
+    got = C16.float().cpu().double()
+    assert torch.isfinite(got).all()
+    err = (got - ref).abs() / (ref.abs() + 1e-2)
+    assert err.max().item() < 2.0 ** -7, err.max().item()
+    assert relerr(got, ref) < 3e-3
+    # without bias, into a wider output (ldc > N is not used by the step, so only the plain layout is exercised)
+    C2 = torch.empty(M, N, dtype=torch.bfloat16, device=DEV)
+    check(lib.tg_proj_bf16(stream_ptr(), ptr(Ad), K, ptr(W16), K, None, ptr(C2), N, M, N, K), "tg_proj_bf16")
+    assert relerr(C2.float().cpu().double(), ref - b.double()) < 3e-3

@@ -313,3 +313,40 @@ def test_inter_layer_dropout_masks_forward_and_bptt():
     assert relerr(dx, ref[0]) < TOL
     for k, gk in enumerate(grads):
         assert relerr(gk, ref[1 + k]) < TOL, f"param {k}"
+
+
+@pytest.mark.parametrize("B,T,H,bt", [(5, 37, 64, 0), (3, 50, 64, 2), (9, 21, 64, 4), (3, 40, 128, 0), (5, 19, 128, 2),
+                                      (6, 13, 128, 4), (256, 768, 64, 0), (256, 768, 128, 0), (512, 768, 128, 0)])
+@pytest.mark.parametrize("save", [True, False])
+def test_forward_from_bf16_gi_is_the_fp32_kernel_on_the_widened_input(B, T, H, bt, save):
+    """tg_gru_fwd_bf16gi (reads the bf16 projection of tg_proj_bf16, saves r,z,n to their own fp32 tensor) does the same
+    arithmetic as tg_gru_fwd on gi16.float(): y, r,z,n and q must come out BIT-identical."""
+    from timegan_b200 import _lib
+    from timegan_b200._lib import lib, check, ptr, stream_ptr
+    DEV = "cuda:0"
+    g = torch.Generator().manual_seed(B * 1000 + T + H)
+    gi16 = (torch.randn(B, T, 3 * H, generator=g)).to(DEV).to(torch.bfloat16)
+    whh = (torch.randn(3 * H, H, generator=g) / H ** 0.5).to(DEV)
+    bhh = (torch.randn(3 * H, generator=g) * 0.1).to(DEV)
+    flags = (_lib.GRU_SAVE if save else 0) | (bt << 8)
+    y0 = torch.empty(B, T, H, device=DEV); q0 = torch.empty(B, T, H, device=DEV) if save else None
+    gi = gi16.float().contiguous()
+    check(lib.tg_gru_fwd(stream_ptr(), ptr(gi), ptr(whh), ptr(bhh), ptr(y0), ptr(q0), B, T, H, flags), "tg_gru_fwd")
+    y1 = torch.full((B, T, H), float("nan"), device=DEV)
+    q1 = torch.full((B, T, H), float("nan"), device=DEV) if save else None
+    rzn = torch.full((B, T, 3 * H), float("nan"), device=DEV) if save else None
+    check(lib.tg_gru_fwd_bf16gi(stream_ptr(), ptr(gi16), ptr(whh), ptr(bhh), ptr(y1), ptr(q1), ptr(rzn), B, T, H, flags),
+          "tg_gru_fwd_bf16gi")
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y0)
+    if save:
+        assert torch.equal(q1, q0) and torch.equal(rzn, gi)
+
+
+def test_bf16_gi_unsupported_hidden_size_is_refused():
+    from timegan_b200._lib import lib, ptr, stream_ptr
+    assert lib.tg_bf16_gi_supported(4096, 64, 64) == 1 and lib.tg_bf16_gi_supported(4096, 128, 128) == 1
+    assert lib.tg_bf16_gi_supported(4096, 24, 24) == 0 and lib.tg_bf16_gi_supported(64, 64, 64) == 0
+    t = torch.zeros(2, 4, 72, device="cuda:0")
+    rc = lib.tg_gru_fwd_bf16gi(stream_ptr(), ptr(t), ptr(t), ptr(t), ptr(t), None, None, 2, 4, 24, 0)
+    assert rc == -4
