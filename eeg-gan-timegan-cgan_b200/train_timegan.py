@@ -428,6 +428,18 @@ def set_step_overlap(on: bool):
     _OVERLAP_STEPS = bool(on)
 
 
+# side streams whose work sits on the step's critical path get a higher CUDA priority: when more CTAs are pending than
+# the SMs have slots (three or four recurrent kernels of 256 CTAs in flight), theirs are dispatched first
+_HIGH_PRIORITY = {4, 5} if os.environ.get("TIMEGAN_B200_STREAM_PRIO", "1") != "0" else set()
+
+
+def _side_stream(device, k: int):
+    pool = _SIDE_STREAMS.setdefault(str(device), [])
+    while len(pool) <= k:
+        pool.append(torch.cuda.Stream(device=device, priority=-1 if len(pool) in _HIGH_PRIORITY else 0))
+    return pool[k]
+
+
 class _Fork:
     """`with _Fork(device, k):` runs the block on side stream k after it has caught up with the current stream.
     The recurrent kernels are latency-bound (768 dependent steps per layer pass) and leave most of each SM idle,
@@ -437,10 +449,7 @@ class _Fork:
     def __init__(self, device, k: int):
         self.main = torch.cuda.current_stream(device)
         if _CONCURRENT:
-            pool = _SIDE_STREAMS.setdefault(str(device), [])
-            while len(pool) <= k:
-                pool.append(torch.cuda.Stream(device=device))
-            self.side = pool[k]
+            self.side = _side_stream(device, k)
         else:
             self.side = self.main
         self.ctx = None
@@ -622,30 +631,62 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
         g_rec = recon_loss(x, x_tilde)
     e_hat = model.gen_latent(z)
     h_hat = model.refine_latent(e_hat)
-    d_in = add_instance_noise(h_hat, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:240 (noise drawn here)
+    # Split backward (only when the caller overlaps this step with disc_step, d_ready given): everything that does not
+    # pass through D -- recon (R <- E), the moment losses (R on the generated latents) and the first-difference term --
+    # is back-propagated BEFORE waiting for D's update, down to h_hat, where its gradient is parked; D's path adds to it
+    # afterwards and only then S and G are unrolled (one BPTT each, as in the single backward).  9 of gen_step's 18 BPTT
+    # passes and their weight gradients thereby run beside disc_step's R1 chain instead of after it.
+    split = d_ready is not None
+    h_use = h_hat.detach().requires_grad_(True) if split else h_hat
+    if split:
+        # D's path gets its own cut point, created on the stream D will run on: autograd accumulates a leaf's gradient
+        # on the stream the leaf was first used on, and that must not be this function's main line (it would then wait
+        # for D's backward before starting the early backward below)
+        fork_adv = _Fork(device, fork_base + 2)
+        with fork_adv:
+            h_adv = h_hat.detach().requires_grad_(True)
+            d_in = add_instance_noise(h_adv, inst_noise_std, nz, _latent_is_gru_view(model))   # tt:240 (noise drawn here)
+    else:
+        d_in = add_instance_noise(h_hat, inst_noise_std, nz, _latent_is_gru_view(model))       # tt:240 (noise drawn here)
     cov_term = torch.zeros((), device=device)
     acf_term = torch.zeros((), device=device)
     fork_dec = _Fork(device, fork_base + 1)
     with fork_dec:                                   # R on the generated latents runs beside D
-        x_hat = model.decode(h_hat)                                                  # tt:251
+        x_hat = model.decode(h_use)                                                  # tt:251
         if gamma_cov > 0 or gamma_acf > 0:                                           # tt:254-263
             cov_term, acf_term = _losses.cov_acf_losses(x_hat, x, acf_max_lag, need_cov=gamma_cov > 0,
                                                         need_acf=gamma_acf > 0)
-    g_sup = sup_loss_fake(h_hat)                                                     # tt:244
-    if d_ready is not None:
-        torch.cuda.current_stream(device).wait_event(d_ready)
-    g_adv = model.discriminator.adv_loss(d_in)       # bce(D(d_in), ones) with D frozen: one head kernel (tt:240-241)
-    fork_rec.join()
-    fork_dec.join()
-    g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
-
-    _zero_grads(optG)
+    g_sup = sup_loss_fake(h_use)                                                     # tt:244
     # buckets in the order their BPTT finishes (recovery, embedder first; then supervisor, generator): each
     # bucket's all-reduce overlaps the BPTT of the networks that are still running
     red = _reducer(model, "G", (model.recovery, model.embedder, model.supervisor, model.generator))
-    if red is not None:
-        red.arm()
-    g_total.backward()
+    if split:
+        # D's forward and dX-only backward on their own stream: they wait for D's update and for d_in, not for the
+        # early backward below (E's and R's BPTT may still be running when S and G are unrolled)
+        with fork_adv:
+            fork_adv.side.wait_event(d_ready)
+            g_adv = model.discriminator.adv_loss(d_in)   # bce(D(d_in), ones) with D frozen (tt:240-241)
+            g_adv.backward()
+        fork_rec.join()
+        fork_dec.join()
+        _zero_grads(optG)
+        if red is not None:
+            red.arm()
+        early = alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
+        early.backward()
+        fork_adv.join()
+        h_hat.backward(h_use.grad + h_adv.grad)
+        with torch.no_grad():
+            g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
+    else:
+        g_adv = model.discriminator.adv_loss(d_in)   # bce(D(d_in), ones) with D frozen: one head kernel (tt:240-241)
+        fork_rec.join()
+        fork_dec.join()
+        g_total = g_adv + alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
+        _zero_grads(optG)
+        if red is not None:
+            red.arm()
+        g_total.backward()
     params = _params(model.generator, model.supervisor, model.embedder, model.recovery)
     _reduce_and_step(optG, params, clip, red)
     nz.end()
@@ -701,25 +742,25 @@ class GraphedJointStep:
         # layer passes) fill the SMs beside disc_step's R1 chain.  Issue order, noise positions and all-reduce call
         # sites are those of the sequential step; only the dependencies the CUDA graph records differ.
         main = torch.cuda.current_stream(self.device)
-        pool = _SIDE_STREAMS.setdefault(str(self.device), [])
-        while len(pool) <= 4:
-            pool.append(torch.cuda.Stream(device=self.device))
-        gstream = pool[4]
+        crit, gstream = _side_stream(self.device, 5), _side_stream(self.device, 6)
         nz = _noise_source(self.noise, self.device)
         hold = hasattr(nz, "hold")
         if hold:
             nz.hold()
         start = torch.cuda.Event()
         start.record(main)
-        d = disc_step(self.model, self.x, self.device, self.optD, k["label_smooth"], std, k["clip"], None,
-                      k["r1_gamma"], target_acc=k["target_acc"], band=k["band"], noise=self.noise, sync=False)
-        d_ready = torch.cuda.Event()
-        d_ready.record(main)
+        crit.wait_event(start)
+        with torch.cuda.stream(crit):         # disc_step's main line (G -> S -> D -> R1 chain) is the step's critical path
+            d = disc_step(self.model, self.x, self.device, self.optD, k["label_smooth"], std, k["clip"], None,
+                          k["r1_gamma"], target_acc=k["target_acc"], band=k["band"], noise=self.noise, sync=False)
+            d_ready = torch.cuda.Event()
+            d_ready.record(crit)
         gstream.wait_event(start)
         with torch.cuda.stream(gstream):
             g = gen_step(self.model, self.x, self.device, self.optG, k["alpha_sup"], k["beta_rec"], std, k["clip"],
                          None, k["gamma_cov"], k["gamma_acf"], k["acf_max_lag"], noise=self.noise, sync=False,
                          d_ready=d_ready, fork_base=2)
+        main.wait_stream(crit)
         main.wait_stream(gstream)
         if hold:
             nz.release()
