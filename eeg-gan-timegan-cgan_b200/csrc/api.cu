@@ -137,6 +137,19 @@ int tg_use_cluster() {
   return x;
 }
 
+// cluster reverse-over-tangent kernel at H = 256 (one group of 8 sequences per 8-CTA cluster): on by default where it
+// is instantiated; TIMEGAN_B200_CLUSTER_JVP256=0 / tg_set_option("cluster_jvp256", 0) keeps the L2-streaming kernel
+static std::atomic<int> g_cluster_jvp256{-1};
+int tg_cluster_jvp256() {
+  int x = g_cluster_jvp256.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_CLUSTER_JVP256");
+    x = (e && atoi(e) == 0) ? 0 : 1;
+    g_cluster_jvp256.store(x);
+  }
+  return x;
+}
+
 // two-columns-per-thread BPTT kernel for one-sequence-per-CTA launches at H <= 64 (gru_bwd.cu): OFF by default -- it
 // halves the shared-memory operand fetches (12 instead of 24 LDS.128 per step) but pays a second shuffle round on the
 // per-step dependency chain, and measured 283 vs 275 us at the c2 layer shape (profiles/r02_probe_bwd_pair.log).
@@ -178,6 +191,7 @@ int tg_device_sm_count(void) { return tg_num_sms(); }
 int tg_set_option(const char* key, int value) {
   if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
   if (key && strcmp(key, "bwd_pair") == 0) { g_bwd_pair.store(value ? 1 : 0); return TG_OK; }
+  if (key && strcmp(key, "cluster_jvp256") == 0) { g_cluster_jvp256.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster") == 0) { g_use_cluster.store(value < 0 || value > 2 ? 1 : value); return TG_OK; }
   if (key && strcmp(key, "peer_timeout_ms") == 0) { g_peer_timeout_ms.store(value < 1 ? 1 : value); return TG_OK; }
   tg_set_error("set_option: unknown key '%s'", key ? key : "(null)");

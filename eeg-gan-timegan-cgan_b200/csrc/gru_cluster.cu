@@ -879,7 +879,7 @@ int max_active_clusters(K kern, int cs, size_t smem) {
   return n;
 }
 
-struct ClCaps { int f128[2], b128[2], j128[2], f256[4], b256[3]; bool ready; };
+struct ClCaps { int f128[2], b128[2], j128[2], f256[4], b256[3], j256[1]; bool ready; };
 ClCaps& cl_caps() {
   static ClCaps c = {};
   if (!c.ready) {
@@ -891,6 +891,7 @@ ClCaps& cl_caps() {
     optin(gru_cl_fwd_kernel<256, 8, 1, 8>); optin(gru_cl_fwd_kernel<256, 8, 2, 8>);
     optin(gru_cl_fwd_kernel<256, 8, 3, 8>); optin(gru_cl_fwd_kernel<256, 8, 4, 8>);
     optin(gru_cl_bwd_kernel<256, 8, 1>); optin(gru_cl_bwd_kernel<256, 8, 2>); optin(gru_cl_bwd_kernel<256, 8, 3, 2>);
+    optin(gru_cl_jvp_bwd_kernel<256, 8, 1>);
     c.f128[0] = max_active_clusters(gru_cl_fwd_kernel<128, 2, 1, 4>, 2, ClFwdSmem<128, 2, 1, 4>::bytes);
     c.f128[1] = max_active_clusters(gru_cl_fwd_kernel<128, 2, 2, 4>, 2, ClFwdSmem<128, 2, 2, 4>::bytes);
     c.b128[0] = max_active_clusters(gru_cl_bwd_kernel<128, 2, 1>, 2, ClBwdSmem<128, 2, 1>::bytes);
@@ -904,6 +905,7 @@ ClCaps& cl_caps() {
     c.b256[0] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 1>, 8, ClBwdSmem<256, 8, 1>::bytes);
     c.b256[1] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 2>, 8, ClBwdSmem<256, 8, 2>::bytes);
     c.b256[2] = max_active_clusters(gru_cl_bwd_kernel<256, 8, 3, 2>, 8, ClBwdSmem<256, 8, 3, 2>::bytes);
+    c.j256[0] = max_active_clusters(gru_cl_jvp_bwd_kernel<256, 8, 1>, 8, ClJbSmem<256, 8, 1>::bytes);
     c.ready = true;
   }
   return c;
@@ -926,6 +928,7 @@ extern "C" int tg_cluster_capacity(int H, int backward, int groups) {
   if (H == 128 && groups >= 1 && groups <= 2) return backward == 2 ? c.j128[groups - 1] : (backward ? c.b128[groups - 1] : c.f128[groups - 1]);
   if (H == 256 && !backward && groups >= 1 && groups <= 4) return c.f256[groups - 1];
   if (H == 256 && backward == 1 && groups >= 1 && groups <= 3) return c.b256[groups - 1];
+  if (H == 256 && backward == 2 && groups == 1) return c.j256[0];
   return 0;
 }
 
@@ -986,9 +989,16 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
 }
 
 // reverse-over-tangent at H = 128: the one-SM kernel (gru_jvp.cu) spills and takes 3.5 ms per call at the c3 shape
+// H = 256: one sequence group per cluster (the six all-gathered vectors of 8 sequences already take 104 KB of shared
+// memory), so only batches that fit ONE wave of resident clusters (15 x 8 = 120 sequences on a B200) go here: 7.9 vs 15.0 ms
+// per pass at B = 120, but 19.2 vs 16.7 ms at B = 256 (three waves; the L2-streaming kernel's time hardly depends on B) --
+// profiles/r02_probe_jvp256.log
 bool tg_cluster_takes_jvp_bwd(int H, int B) {
-  (void)B;
-  return tg_use_cluster() != 0 && H == 128;
+  const int mode = tg_use_cluster();
+  if (mode == 0) return false;
+  if (H == 128) return true;
+  if (H != 256 || cl_caps().j256[0] <= 0) return false;
+  return mode == 2 || (tg_cluster_jvp256() && (B + 7) / 8 <= cl_caps().j256[0]);
 }
 
 int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, const float* rzn, const float* q,
@@ -996,6 +1006,7 @@ int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, co
                       float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only) {
   ClJbParams p{hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, last_only};
   if (H == 128) return pick_groups(B, 4, cl_caps().j128, 2) == 1 ? launch_cl_jb<128, 2, 1>(st, p) : launch_cl_jb<128, 2, 2>(st, p);
+  if (H == 256) return launch_cl_jb<256, 8, 1>(st, p);
   tg_set_error("gru_cl_jvp_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }
