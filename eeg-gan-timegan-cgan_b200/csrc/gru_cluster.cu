@@ -41,6 +41,14 @@ namespace {
 
 constexpr int CL_THREADS = 256;
 constexpr int CL_PF = 4;          // prefetch distance (timesteps) of the cp.async input ring
+// Experiment kept as a compile-time switch (off): issuing a step's HBM traffic from inside the first group's mat-vec so
+// that it rides in the FMA pipe's free issue slots.  Measured SLOWER on a B200 (H = 128, B = 256: forward 765 -> 881 us,
+// BPTT 1058 -> 1123 us per pass): the extra shared-memory reads and global stores land in the middle of the operand
+// stream the FFMA2s are waiting on.
+#ifndef TG_CL_IO_IN_MATVEC
+#define TG_CL_IO_IN_MATVEC 0
+#endif
+constexpr bool CL_IO_IN_MATVEC = TG_CL_IO_IN_MATVEC != 0;
 constexpr int CL_HPAD = 16;       // state rows are H+16 floats apart (bank spread between the sequences of a lane group)
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -250,8 +258,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   for (int t = 0; t < T; ++t) {
     cp_async_wait<CL_PF - 2>();          // this thread's share of step t's gi rows has landed
     __syncthreads();                     // ... and everybody else's; also closes step t-1's staging writes
-    if (t > 0) store(t - 1);             // outputs of step t-1: coalesced float4 rows
-    prefetch(t + CL_PF - 1);
+    // The step's HBM traffic (outputs of step t-1 as coalesced float4 rows, cp.async of step t+PF-1's inputs) is issued
+    // from INSIDE the first group's mat-vec: FFMA2 occupies the scheduler's issue port every other cycle only, so the
+    // loads / stores / address arithmetic ride in the free slots instead of standing between two barriers.
+    if (!CL_IO_IN_MATVEC) {
+      if (t > 0) store(t - 1);
+      prefetch(t + CL_PF - 1);
+    }
     const int par = t & 1, ppar = par ^ 1;
     float* sgw = stg + par * (BT * 5 * HU);
     const float* ringt = ring + (t % CL_PF) * (BT * 3 * HU);
@@ -319,6 +332,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 #pragma unroll
           for (int b = 0; b < SG; ++b)
             hv[(i + 1) & 1][b] = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)((i + 1) * G) * 16u);
+        }
+        if (CL_IO_IN_MATVEC && grp == 0 && i == 1) {
+          if (t > 0) store(t - 1);
+          prefetch(t + CL_PF - 1);
         }
 #pragma unroll
         for (int b = 0; b < SG; ++b) {
@@ -488,8 +505,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     const int t = T - 1 - s;
     cp_async_wait<PF - 2>();
     __syncthreads();
-    if (s > 0) store(t + 1, s - 1);      // outputs of step t+1
-    prefetch(t - (PF - 1));
+    if (!CL_IO_IN_MATVEC || s == 0) {    // (the first step has no mat-vec to hide the I/O behind)
+      if (s > 0) store(t + 1, s - 1);    // outputs of step t+1
+      prefetch(t - (PF - 1));
+    }
     const int par = s & 1, ppar = par ^ 1;
     float* sgw = stg + par * (BT * 4 * HU);
 #pragma unroll
@@ -522,6 +541,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 #pragma unroll
             for (int b = 0; b < G; ++b)
               dvv[(it + 1) & 1][b] = lds_v4(dc + (uint32_t)((b * 3 + g1) * HR) * 4u + (uint32_t)(i1 * L2) * 16u);
+          }
+          if (CL_IO_IN_MATVEC && grp == 0 && it == 1) {      // this step's HBM traffic rides in the mat-vec's free issue slots
+            store(t + 1, s - 1);
+            prefetch(t - (PF - 1));
           }
 #pragma unroll
           for (int b = 0; b < G; ++b) {
