@@ -430,13 +430,16 @@ def set_step_overlap(on: bool):
 
 # side streams whose work sits on the step's critical path get a higher CUDA priority: when more CTAs are pending than
 # the SMs have slots (three or four recurrent kernels of 256 CTAs in flight), theirs are dispatched first
-_HIGH_PRIORITY = {4, 5} if os.environ.get("TIMEGAN_B200_STREAM_PRIO", "1") != "0" else set()
+# (pool index -> priority; 0 is CUDA's lowest).  4 = D's path inside gen_step, 5 = disc_step's main line.  A third level
+# (the recon path of gen_step below everything else, its backward issued from a helper stream so that S and G need not
+# wait for it) measured the same 20.5 ms/step: the step is bound by SM throughput, not by the order of the fill-in work.
+_STREAM_PRIORITY = {4: -1, 5: -1} if os.environ.get("TIMEGAN_B200_STREAM_PRIO", "1") != "0" else {}
 
 
 def _side_stream(device, k: int):
     pool = _SIDE_STREAMS.setdefault(str(device), [])
     while len(pool) <= k:
-        pool.append(torch.cuda.Stream(device=device, priority=-1 if len(pool) in _HIGH_PRIORITY else 0))
+        pool.append(torch.cuda.Stream(device=device, priority=_STREAM_PRIORITY.get(len(pool), 0)))
     return pool[k]
 
 
@@ -662,16 +665,16 @@ def gen_step(model: TimeGAN, x, device, optG, alpha_sup, beta_rec, inst_noise_st
     red = _reducer(model, "G", (model.recovery, model.embedder, model.supervisor, model.generator))
     if split:
         # D's forward and dX-only backward on their own stream: they wait for D's update and for d_in, not for the
-        # early backward below (E's and R's BPTT may still be running when S and G are unrolled)
+        # early backward below (whatever is left of it runs beside them)
         with fork_adv:
             fork_adv.side.wait_event(d_ready)
             g_adv = model.discriminator.adv_loss(d_in)   # bce(D(d_in), ones) with D frozen (tt:240-241)
             g_adv.backward()
-        fork_rec.join()
-        fork_dec.join()
         _zero_grads(optG)
         if red is not None:
             red.arm()
+        fork_rec.join()
+        fork_dec.join()
         early = alpha_sup * g_sup + beta_rec * g_rec + gamma_cov * cov_term + gamma_acf * acf_term
         early.backward()
         fork_adv.join()

@@ -28,6 +28,7 @@ def short(name: str) -> str:
                 "sumsq_multi", "bigh_"):
         if key in name:
             return key
+    name = name.replace("(anonymous namespace)::", "").replace("void ", "")
     return name.split("(")[0].split("<")[0][-40:]
 
 
