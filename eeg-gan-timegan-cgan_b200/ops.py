@@ -366,8 +366,10 @@ def stack_jvp_forward(xdot: torch.Tensor, saves: List[LayerSave], weights: Seque
         w_ih, w_hh, _, _ = _layer_weights(weights, l)
         H = w_hh.shape[1]
         gid = torch.empty(B, T, 3 * H, dtype=torch.float32, device=dev)
+        # the R1 tangent keeps fp32-parity precision in the reduced-precision modes too (3xTF32 on the tensor pipe;
+        # it used to fall back to the FFMA kernel there: 424 vs 140 us per call at the c3 shape)
         proj(tin.view(B * T, -1), w_ih, None, gid.view(B * T, 3 * H),
-             mode=_lib.PROJ_FP32 if _PROJ_MODE == _lib.PROJ_TF32 else _PROJ_MODE)
+             mode=_lib.PROJ_TF32X3 if _PROJ_MODE == _lib.PROJ_TF32 else _PROJ_MODE)
         ydot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         qdot = torch.empty(B, T, H, dtype=torch.float32, device=dev)
         check(lib.tg_gru_jvp_fwd(stream_ptr(), ptr(gid), ptr(sv.rzn), ptr(sv.q), ptr(sv.y), ptr(w_hh), ptr(ydot),

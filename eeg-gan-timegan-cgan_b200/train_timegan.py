@@ -840,7 +840,8 @@ def train_single_npz(npz_path: Path, out_dir: Path,
                      stop_after: Optional[int] = None):
     """Same schedule, logs and artefacts as the reference.  Extras (keyword-only): `z_dim`/`hidden_dim`
     override adaptive_dims; `noise="host"` replays the reference's CPU random stream (parity runs), default is
-    on-device Philox; `proj_dtype` "fp32" | "bf16" (tensor-core input projections).
+    on-device Philox; `proj_dtype` "fp32" | "bf16" (bf16 input projections with a bf16 gi tensor, one TF32 pass
+    for dX / weight gradients) | "tf32" (one TF32 pass everywhere).
     The default path is the fast path: every step still gets its CSV row and the reference's per-step
     best-checkpoint rule is still applied to every step (on the device, `BestSnapshot`), but the host only
     synchronises with the GPU every `log_every` steps (default 25; 1 with host-replayed noise) to write the rows
@@ -1083,7 +1084,7 @@ def build_argparser():
     # extras of this implementation (defaults = reference behaviour)
     ap.add_argument("--z_dim", type=int, default=None, help="override adaptive_dims' latent size")
     ap.add_argument("--hidden_dim", type=int, default=None, help="override adaptive_dims' hidden size")
-    ap.add_argument("--proj_dtype", type=str, default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--proj_dtype", type=str, default="fp32", choices=["fp32", "bf16", "tf32"])
     ap.add_argument("--noise", type=str, default=None, choices=[None, "host"])
     ap.add_argument("--log_every", type=int, default=None,
                     help="GAN steps between host synchronisations (CSV rows are per step either way); default 25")

@@ -15,6 +15,7 @@ def main():
     ap.add_argument("--layers", type=int, default=3)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--proj", type=str, default="fp32")
+    ap.add_argument("--eager", action="store_true", help="issue the joint step eagerly instead of replaying the CUDA graph")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -57,14 +58,24 @@ def main():
         ae = timed(lambda x: tt.phase_autoencoder(m, [(x,)], dev, oER, 0.5, 1, log), xg)
         sup = timed(lambda x: tt.phase_supervisor(m, [(x,)], dev, oS, 0.5, 1, log), xg)
 
-        def joint(x):
-            tt.disc_step(m, x, dev, oD, 0.2, 0.3, 0.5, None, 1.0, target_acc=0.525, band=0.15, sync=False)
-            tt.gen_step(m, x, dev, oG, 5.0, 0.2, 0.3, 0.5, None, 0.05, 0.05, 64, sync=False)
+        # the joint phase as train_single_npz runs it by default: replayed from the CUDA graph (capturable optimisers)
+        oDg = tg.FusedAdam(m.discriminator.parameters(), lr=2e-4, betas=(0.5, 0.9), capturable=True)
+        oGg = tg.FusedAdam(P(m.generator, m.supervisor, m.embedder, m.recovery), lr=1e-3, betas=(0.5, 0.9), capturable=True)
+        use_graph = not a.eager and (world == 1 or D.peer_comm() is not None)
+        if use_graph:
+            gj = tt.GraphedJointStep(m, oDg, oGg, dev, label_smooth=0.2, clip=0.5, r1_gamma=1.0, target_acc=0.525, band=0.15,
+                                     alpha_sup=5.0, beta_rec=0.2, gamma_cov=0.05, gamma_acf=0.05, acf_max_lag=64, warmup=2)
+            joint = lambda x: gj(x, 0.3)
+        else:
+            def joint(x):
+                tt.disc_step(m, x, dev, oD, 0.2, 0.3, 0.5, None, 1.0, target_acc=0.525, band=0.15, sync=False)
+                tt.gen_step(m, x, dev, oG, 5.0, 0.2, 0.3, 0.5, None, 0.05, 0.05, 64, sync=False)
         jt = timed(joint)
+        del oDg, oGg
         if rank == 0:
             g = B * world
             print(json.dumps({"hidden": H, "layers": a.layers, "batch_per_gpu": B, "n_gpus": world, "proj": a.proj,
-                              "issue": "eager",
+                              "issue": "AE/SUP eager, joint " + ("cuda-graph replay" if use_graph else "eager"),
                               "ae_seq_s": round(g / ae * 1e3, 1), "sup_seq_s": round(g / sup * 1e3, 1),
                               "joint_seq_s": round(g / jt * 1e3, 1), "ae_ms": round(ae, 2), "sup_ms": round(sup, 2),
                               "joint_ms": round(jt, 2)}), flush=True)
