@@ -143,8 +143,13 @@ template <int H, int CS, int NGRP, int SG>
 struct ClFwdSmem {
   static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = SG * NGRP, HR = H + CL_HPAD;
   static constexpr int HBUF = 2 * BT * HR;             // floats
-  static constexpr int RING = CL_PF * BT * 3 * HU;     // floats
-  static constexpr int STG = 2 * BT * 5 * HU;          // floats
+  // Per-sequence blocks of the input ring / output staging are padded by 32/G floats: the lanes of a warp that work on
+  // the same column of DIFFERENT sequences (G of them) would otherwise hit one bank -- (arrays x HU) is a multiple of 32
+  // floats -- a G-way conflict on every per-step load of the saved activations and every staging store (ncu counted
+  // 26.8 M shared-memory bank conflicts per BPTT launch at H = 128, against ~1 M in the one-SM kernels).
+  static constexpr int SPAD = 32 / G, RSEQ = 3 * HU + SPAD, SSEQ = 5 * HU + SPAD;
+  static constexpr int RING = CL_PF * BT * RSEQ;       // floats
+  static constexpr int STG = 2 * BT * SSEQ;            // floats
   static constexpr size_t bytes = (size_t)(HBUF + RING + STG) * 4 + 128;
 };
 
@@ -179,14 +184,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   constexpr int Q = HU / 4;                               // float4 per row segment
   constexpr int NLI = BT * 3 * Q, NSI = BT * 5 * Q;       // load / store items per step
   constexpr int NLD = (NLI + CL_THREADS - 1) / CL_THREADS, NSD = (NSI + CL_THREADS - 1) / CL_THREADS;
-  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * 3 * HU) * 4u, STG_BYTES = (uint32_t)(BT * 5 * HU) * 4u;
+  constexpr int RSEQ = S::RSEQ, SSEQ = S::SSEQ;
+  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * RSEQ) * 4u, STG_BYTES = (uint32_t)(BT * SSEQ) * 4u;
   const float* lp[NLD]; uint32_t ls[NLD]; bool lv[NLD];
 #pragma unroll
   for (int m = 0; m < NLD; ++m) {
     const int n = tid + CL_THREADS * m, j4 = n % Q, g = (n / Q) % 3, b = n / (3 * Q);
     lv[m] = (n < NLI) && (b0 + b < p.B);
     lp[m] = p.gi + (size_t)(b0 + (lv[m] ? b : 0)) * T * (3 * H) + g * H + (int)rank * HU + j4 * 4;
-    ls[m] = smem_u32(ring) + (uint32_t)((b * 3 + g) * HU + j4 * 4) * 4u;
+    ls[m] = smem_u32(ring) + (uint32_t)(b * RSEQ + g * HU + j4 * 4) * 4u;
   }
   float* sp[NSD]; uint32_t ss[NSD]; bool sv[NSD]; int sst[NSD];
 #pragma unroll
@@ -197,7 +203,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     float* base = (wch < 3) ? p.gi + seq * (3 * H) + wch * H : (wch == 3 ? p.q + seq * H : p.y + seq * H);
     sp[m] = base + (int)rank * HU + j4 * 4;
     sst[m] = (wch < 3) ? 3 * H : H;
-    ss[m] = smem_u32(stg) + (uint32_t)((b * 5 + wch) * HU + j4 * 4) * 4u;
+    ss[m] = smem_u32(stg) + (uint32_t)(b * SSEQ + wch * HU + j4 * 4) * 4u;
   }
   auto prefetch = [&](int t) {
     if (t < T) {
@@ -266,11 +272,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
       prefetch(t + CL_PF - 1);
     }
     const int par = t & 1, ppar = par ^ 1;
-    float* sgw = stg + par * (BT * 5 * HU);
-    const float* ringt = ring + (t % CL_PF) * (BT * 3 * HU);
+    float* sgw = stg + par * (BT * SSEQ);
+    const float* ringt = ring + (t % CL_PF) * (BT * RSEQ);
     // everything after a group's mat-vec: combine the lane partials, gates, state update, all-gather, staging
     auto post = [&](const int grp, float2 (&acc)[SG][3]) __attribute__((always_inline)) {
-      const float* gr_ = ringt + ((grp * SG + ob) * 3) * HU + jl;
+      const float* gr_ = ringt + (grp * SG + ob) * RSEQ + jl;
       const float gr = gr_[0], gz = gr_[HU], gn = gr_[2 * HU];
       float own[3];
 #pragma unroll
@@ -297,7 +303,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
           if (r_ok[d]) st_async_v4(r_h[d] + off, h0, h1, h2, h3, r_bar[d] + (uint32_t)(grp * 2 + par) * 8u);
       }
       if (primary) {
-        float* so = sgw + ((grp * SG + ob) * 5) * HU + jl;
+        float* so = sgw + (grp * SG + ob) * SSEQ + jl;
         so[0] = r; so[HU] = z; so[2 * HU] = n; so[3 * HU] = qv; so[4 * HU] = h;
       }
     };
@@ -376,8 +382,9 @@ template <int H, int CS, int NGRP, int PF = CL_PF>
 struct ClBwdSmem {
   static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
   static constexpr int DBUF = 2 * BT * 3 * HR;         // floats: dGH vectors, double-buffered
-  static constexpr int RING = PF * BT * 6 * HU;        // r,z,n,q,h_{t-1},dy
-  static constexpr int STG = 2 * BT * 4 * HU;          // dar,daz,dan,dq
+  static constexpr int SPAD = 32 / G, RSEQ = 6 * HU + SPAD, SSEQ = 4 * HU + SPAD;   // padded per-sequence blocks (see ClFwdSmem)
+  static constexpr int RING = PF * BT * RSEQ;          // r,z,n,q,h_{t-1},dy
+  static constexpr int STG = 2 * BT * SSEQ;            // dar,daz,dan,dq
   static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
 };
 
@@ -415,7 +422,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   constexpr int Q = HU / 4;
   constexpr int NLI = BT * 6 * Q, NSI = BT * 4 * Q;
   constexpr int NLD = (NLI + CL_THREADS - 1) / CL_THREADS, NSD = (NSI + CL_THREADS - 1) / CL_THREADS;
-  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * 6 * HU) * 4u, STG_BYTES = (uint32_t)(BT * 4 * HU) * 4u;
+  constexpr int RSEQ = S::RSEQ, SSEQ = S::SSEQ;
+  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * RSEQ) * 4u, STG_BYTES = (uint32_t)(BT * SSEQ) * 4u;
   const float* lp[NLD]; uint32_t ls[NLD]; bool lv[NLD]; int lst[NLD]; bool lshift[NLD];
 #pragma unroll
   for (int m = 0; m < NLD; ++m) {
@@ -429,7 +437,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     if (wch == 5 && !p.dy_last) base = p.dy + seq * H;
     lp[m] = base + col;
     lst[m] = (wch < 3) ? 3 * H : H;
-    ls[m] = smem_u32(ring) + (uint32_t)((b * 6 + wch) * HU + j4 * 4) * 4u;
+    ls[m] = smem_u32(ring) + (uint32_t)(b * RSEQ + wch * HU + j4 * 4) * 4u;
   }
   float* sp[NSD]; uint32_t ss[NSD]; bool sv[NSD]; int sst[NSD];
 #pragma unroll
@@ -439,7 +447,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     const size_t seq = (size_t)(b0 + (sv[m] ? b : 0)) * T;
     sp[m] = ((wch < 3) ? p.dgi + seq * (3 * H) + wch * H : p.dq + seq * H) + (int)rank * HU + j4 * 4;
     sst[m] = (wch < 3) ? 3 * H : H;
-    ss[m] = smem_u32(stg) + (uint32_t)((b * 4 + wch) * HU + j4 * 4) * 4u;
+    ss[m] = smem_u32(stg) + (uint32_t)(b * SSEQ + wch * HU + j4 * 4) * 4u;
   }
   auto prefetch = [&](int t) {         // t counts down; t < 0: nothing to load
     if (t >= 0) {
@@ -510,11 +518,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
       prefetch(t - (PF - 1));
     }
     const int par = s & 1, ppar = par ^ 1;
-    float* sgw = stg + par * (BT * 4 * HU);
+    float* sgw = stg + par * (BT * SSEQ);
 #pragma unroll
     for (int grp = 0; grp < NGRP; ++grp) {
       // saved activations of (b, t, k): everything that does not depend on the carried dh first
-      const float* rg = ring + (((t % PF) * BT + grp * G + ob) * 6) * HU + kl;
+      const float* rg = ring + ((t % PF) * BT + grp * G + ob) * RSEQ + kl;
       const float r = rg[0], z = rg[HU], n = rg[2 * HU], qv = rg[3 * HU], dyv = rg[5 * HU];
       const float hp = (t == 0) ? 0.f : rg[4 * HU];          // h_{-1} = 0 (row -1 is never loaded; the slot is stale)
       const float omz = 1.f - z;
@@ -589,7 +597,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
             st_async_v4(r_d[d] + off + 2u * (uint32_t)HR * 4u, vq[0], vq[1], vq[2], vq[3], bar);
           }
       }
-      float* so = sgw + ((grp * G + ob) * 4) * HU + kl;
+      float* so = sgw + (grp * G + ob) * SSEQ + kl;
       so[0] = dar; so[HU] = daz; so[2 * HU] = dan; so[3 * HU] = dqv;
     }
   }
@@ -628,8 +636,9 @@ template <int H, int CS, int NGRP>
 struct ClJbSmem {
   static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
   static constexpr int DBUF = 2 * BT * 6 * HR;
-  static constexpr int RING = CL_PF * BT * 12 * HU;    // r,z,n,q, ar,az,an,qd, h_{t-1}, hd_{t-1}, hbar, hdbar
-  static constexpr int STG = 2 * BT * 8 * HU;          // arb,azb,anb,qb, arb_d,azb_d,anb_d,qdb
+  static constexpr int SPAD = 32 / G, RSEQ = 12 * HU + SPAD, SSEQ = 8 * HU + SPAD;  // padded per-sequence blocks (see ClFwdSmem)
+  static constexpr int RING = CL_PF * BT * RSEQ;       // r,z,n,q, ar,az,an,qd, h_{t-1}, hd_{t-1}, hbar, hdbar
+  static constexpr int STG = 2 * BT * SSEQ;            // arb,azb,anb,qb, arb_d,azb_d,anb_d,qdb
   static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
 };
 
@@ -665,7 +674,8 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   constexpr int Q = HU / 4;
   constexpr int NLI = BT * 12 * Q, NSI = BT * 8 * Q;
   constexpr int NLD = (NLI + CL_THREADS - 1) / CL_THREADS, NSD = (NSI + CL_THREADS - 1) / CL_THREADS;
-  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * 12 * HU) * 4u, STG_BYTES = (uint32_t)(BT * 8 * HU) * 4u;
+  constexpr int RSEQ = S::RSEQ, SSEQ = S::SSEQ;
+  constexpr uint32_t SLOT_BYTES = (uint32_t)(BT * RSEQ) * 4u, STG_BYTES = (uint32_t)(BT * SSEQ) * 4u;
   const float* lp[NLD]; uint32_t ls[NLD]; bool lv[NLD]; int lst[NLD]; bool lshift[NLD];
 #pragma unroll
   for (int m = 0; m < NLD; ++m) {
@@ -684,7 +694,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     else if (!p.last_only) base = (wch == 10 ? p.hbar : p.hdbar) + seq * H;
     lp[m] = base + col;
     lst[m] = (wch < 3 || (wch >= 4 && wch < 7)) ? 3 * H : H;
-    ls[m] = smem_u32(ring) + (uint32_t)((b * 12 + wch) * HU + j4 * 4) * 4u;
+    ls[m] = smem_u32(ring) + (uint32_t)(b * RSEQ + wch * HU + j4 * 4) * 4u;
   }
   float* sp[NSD]; uint32_t ss[NSD]; bool sv[NSD]; int sst[NSD];
 #pragma unroll
@@ -696,7 +706,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
                   : (wch == 3 ? p.qb + seq * H : (wch < 7 ? p.gidb + seq * (3 * H) + (wch - 4) * H : p.qdb + seq * H));
     sp[m] = base + (int)rank * HU + j4 * 4;
     sst[m] = (wch < 3 || (wch >= 4 && wch < 7)) ? 3 * H : H;
-    ss[m] = smem_u32(stg) + (uint32_t)((b * 8 + wch) * HU + j4 * 4) * 4u;
+    ss[m] = smem_u32(stg) + (uint32_t)(b * SSEQ + wch * HU + j4 * 4) * 4u;
   }
   auto prefetch = [&](int t) {
     if (t >= 0) {
@@ -763,11 +773,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     if (s > 0) store(t + 1, s - 1);
     prefetch(t - (CL_PF - 1));
     const int par = s & 1, ppar = par ^ 1;
-    float* sgw = stg + par * (BT * 8 * HU);
+    float* sgw = stg + par * (BT * SSEQ);
 #pragma unroll
     for (int grp = 0; grp < NGRP; ++grp) {
       // ---- coefficient pairs of (b, t, k): out = alpha hb + beta hdb ----
-      const float* rg = ring + (((t % CL_PF) * BT + grp * G + ob) * 12) * HU + kl;
+      const float* rg = ring + ((t % CL_PF) * BT + grp * G + ob) * RSEQ + kl;
       const float rt = rg[0], zt = rg[HU], nt = rg[2 * HU], qt = rg[3 * HU];
       const float art = rg[4 * HU], azt = rg[5 * HU], ant = rg[6 * HU], qdt = rg[7 * HU];
       const float hp = (t == 0) ? 0.f : rg[8 * HU], hdp = (t == 0) ? 0.f : rg[9 * HU];
@@ -842,7 +852,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
               st_async_v4(r_d[d] + off + (uint32_t)(e * HR) * 4u, v0, v1, v2, v3, r_bar[d] + (uint32_t)(grp * 2 + par) * 8u);
         }
       }
-      float* so = sgw + ((grp * G + ob) * 8) * HU + kl;
+      float* so = sgw + (grp * G + ob) * SSEQ + kl;
       so[0] = arb; so[HU] = azb; so[2 * HU] = anb; so[3 * HU] = qb;
       so[4 * HU] = arb_d; so[5 * HU] = azb_d; so[6 * HU] = anb_d; so[7 * HU] = qdb;
     }
