@@ -150,6 +150,21 @@ int tg_cluster_jvp256() {
   return x;
 }
 
+// direct-I/O variant of the cluster BPTT kernel (registers instead of the shared-memory input ring / output staging, no
+// block barrier per step).  OFF: measured slower on a B200 (H = 128, B = 256: 1302 vs 1057 us per pass) -- the per-lane
+// global loads / stores (four 32-byte sectors per warp instruction) go through the same LSU pipe as the mat-vec's LDS.128
+// operand stream, which is what the kernel waits on.  TIMEGAN_B200_CLUSTER_DIO=1 / tg_set_option("cluster_dio", 1).
+static std::atomic<int> g_cluster_dio{-1};
+int tg_cluster_dio() {
+  int x = g_cluster_dio.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_CLUSTER_DIO");
+    x = (e && atoi(e) != 0) ? 1 : 0;
+    g_cluster_dio.store(x);
+  }
+  return x;
+}
+
 // two-columns-per-thread BPTT kernel for one-sequence-per-CTA launches at H <= 64 (gru_bwd.cu): OFF by default -- it
 // halves the shared-memory operand fetches (12 instead of 24 LDS.128 per step) but pays a second shuffle round on the
 // per-step dependency chain, and measured 283 vs 275 us at the c2 layer shape (profiles/r02_probe_bwd_pair.log).
@@ -191,6 +206,7 @@ int tg_device_sm_count(void) { return tg_num_sms(); }
 int tg_set_option(const char* key, int value) {
   if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
   if (key && strcmp(key, "bwd_pair") == 0) { g_bwd_pair.store(value ? 1 : 0); return TG_OK; }
+  if (key && strcmp(key, "cluster_dio") == 0) { g_cluster_dio.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster_jvp256") == 0) { g_cluster_jvp256.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster") == 0) { g_use_cluster.store(value < 0 || value > 2 ? 1 : value); return TG_OK; }
   if (key && strcmp(key, "peer_timeout_ms") == 0) { g_peer_timeout_ms.store(value < 1 ? 1 : value); return TG_OK; }

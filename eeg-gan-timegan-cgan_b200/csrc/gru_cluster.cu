@@ -378,19 +378,26 @@ struct ClBwdParams {
 };
 
 // PF = depth of the input ring (prefetch distance PF-1 steps); 2 where three groups per cluster leave no room for 4
-template <int H, int CS, int NGRP, int PF = CL_PF>
+// DIO ("direct I/O"): no input ring, no output staging, no block barrier in the loop -- every lane loads the six saved
+// values of ITS (sequence, column) for step t-1 straight from global memory into registers while step t runs (the lanes
+// of a warp cover 32-byte sectors completely: 32/G consecutive columns x G sequences), and stores its four outputs
+// directly.  The only synchronisation left per step is the mbarrier of the all-gathered dGH vector.  The WAR hazard on
+// the double-buffered dGH vectors is closed by data dependence exactly as between CTAs: a warp can send step s+1's
+// values only after it has received step s's values from EVERY warp of the cluster, and a warp sends those after its
+// step-s mat-vec, i.e. after its last read of the buffer that step s+1 overwrites.
+template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false>
 struct ClBwdSmem {
   static constexpr int HU = H / CS, G = CL_THREADS / HU, BT = G * NGRP, HR = H + CL_HPAD;
   static constexpr int DBUF = 2 * BT * 3 * HR;         // floats: dGH vectors, double-buffered
   static constexpr int SPAD = 32 / G, RSEQ = 6 * HU + SPAD, SSEQ = 4 * HU + SPAD;   // padded per-sequence blocks (see ClFwdSmem)
-  static constexpr int RING = PF * BT * RSEQ;          // r,z,n,q,h_{t-1},dy
-  static constexpr int STG = 2 * BT * SSEQ;            // dar,daz,dan,dq
+  static constexpr int RING = DIO ? 0 : PF * BT * RSEQ;          // r,z,n,q,h_{t-1},dy
+  static constexpr int STG = DIO ? 0 : 2 * BT * SSEQ;            // dar,daz,dan,dq
   static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
 };
 
-template <int H, int CS, int NGRP, int PF = CL_PF>
+template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams p) {
-  using S = ClBwdSmem<H, CS, NGRP, PF>;
+  using S = ClBwdSmem<H, CS, NGRP, PF, DIO>;
   constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR;
   constexpr int L2 = 2 * G;            // lanes per output pair
   constexpr int J = H / L2;            // j values per lane and gate
@@ -408,7 +415,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   const int kl = 2 * kp + oo;                      // its output column inside the CTA's slice
   const int k = (int)rank * HU + kl;
 
-  for (int i = tid; i < S::DBUF + S::RING; i += CL_THREADS) dbuf[i] = 0.f;
+  for (int i = tid; i < S::DBUF + S::RING; i += CL_THREADS) dbuf[i] = 0.f;     // (DIO: RING = 0)
   constexpr uint32_t TXB = (uint32_t)(3 * H * G * 4);
   if (tid == 0) {
     for (int i = 0; i < 2 * NGRP; ++i) mbar_init(&bars[i], 1);
@@ -464,7 +471,35 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     for (int m = 0; m < NSD; ++m)
       if (sv[m]) *reinterpret_cast<float4*>(sp[m] + (size_t)t * sst[m]) = lds_v4(ss[m] + so);
   };
-  for (int s = 0; s < PF - 1; ++s) prefetch(T - 1 - s);
+  if (!DIO)
+    for (int s = 0; s < PF - 1; ++s) prefetch(T - 1 - s);
+
+  // ---- DIO: this lane's saved activations of step t (cur) and t-1 (nxt), per sequence group ----
+  struct Saved { float r, z, n, q, hp, dy; };
+  Saved cur[NGRP], nxt[NGRP];
+  bool seq_ok[NGRP];
+  size_t row0[NGRP];                      // (b0 + grp*G + ob) * T
+#pragma unroll
+  for (int g = 0; g < NGRP; ++g) {
+    seq_ok[g] = (b0 + g * G + ob) < p.B;
+    row0[g] = (size_t)(b0 + (seq_ok[g] ? g * G + ob : 0)) * T;
+  }
+  auto load_saved = [&](int g, int t) {
+    Saved v = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (seq_ok[g] && t >= 0) {
+      const size_t row = row0[g] + (size_t)t;
+      const float* a = p.rzn + row * (3 * H) + k;
+      v.r = __ldg(a); v.z = __ldg(a + H); v.n = __ldg(a + 2 * H);
+      v.q = __ldg(p.q + row * H + k);
+      if (t > 0) v.hp = __ldg(p.y + (row - 1) * H + k);
+      if (!p.dy_last) v.dy = __ldg(p.dy + row * H + k);
+    }
+    return v;
+  };
+  if (DIO) {
+#pragma unroll
+    for (int g = 0; g < NGRP; ++g) cur[g] = load_saved(g, T - 1);
+  }
 
   // =============================== compute warps ===============================
   // ---- W_hh^T slices: wt[o][g][m] = (W[gH+jj][k0+o], W[gH+jj+1][k0+o]),  jj = (i*L2+ql)*4 + 2*(m&1), i = m>>1 ----
@@ -511,20 +546,30 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 
   for (int s = 0; s < T; ++s) {
     const int t = T - 1 - s;
-    cp_async_wait<PF - 2>();
-    __syncthreads();
-    if (!CL_IO_IN_MATVEC || s == 0) {    // (the first step has no mat-vec to hide the I/O behind)
-      if (s > 0) store(t + 1, s - 1);    // outputs of step t+1
-      prefetch(t - (PF - 1));
+    if (!DIO) {
+      cp_async_wait<PF - 2>();
+      __syncthreads();
+      if (!CL_IO_IN_MATVEC || s == 0) {    // (the first step has no mat-vec to hide the I/O behind)
+        if (s > 0) store(t + 1, s - 1);    // outputs of step t+1
+        prefetch(t - (PF - 1));
+      }
+    } else {
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) nxt[g] = load_saved(g, t - 1);     // in flight for the whole step
     }
     const int par = s & 1, ppar = par ^ 1;
     float* sgw = stg + par * (BT * SSEQ);
 #pragma unroll
     for (int grp = 0; grp < NGRP; ++grp) {
       // saved activations of (b, t, k): everything that does not depend on the carried dh first
-      const float* rg = ring + ((t % PF) * BT + grp * G + ob) * RSEQ + kl;
-      const float r = rg[0], z = rg[HU], n = rg[2 * HU], qv = rg[3 * HU], dyv = rg[5 * HU];
-      const float hp = (t == 0) ? 0.f : rg[4 * HU];          // h_{-1} = 0 (row -1 is never loaded; the slot is stale)
+      float r, z, n, qv, dyv, hp;
+      if (DIO) {
+        r = cur[grp].r; z = cur[grp].z; n = cur[grp].n; qv = cur[grp].q; dyv = cur[grp].dy; hp = cur[grp].hp;
+      } else {
+        const float* rg = ring + ((t % PF) * BT + grp * G + ob) * RSEQ + kl;
+        r = rg[0]; z = rg[HU]; n = rg[2 * HU]; qv = rg[3 * HU]; dyv = rg[5 * HU];
+        hp = (t == 0) ? 0.f : rg[4 * HU];          // h_{-1} = 0 (row -1 is never loaded; the slot is stale)
+      }
       const float omz = 1.f - z;
       const float fA = omz * fmaf(-n, n, 1.f);
       const float fB = (hp - n) * (z * omz);
@@ -597,13 +642,28 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
             st_async_v4(r_d[d] + off + 2u * (uint32_t)HR * 4u, vq[0], vq[1], vq[2], vq[3], bar);
           }
       }
-      float* so = sgw + (grp * G + ob) * SSEQ + kl;
-      so[0] = dar; so[HU] = daz; so[2 * HU] = dan; so[3 * HU] = dqv;
+      if (DIO) {
+        if (seq_ok[grp]) {
+          const size_t row = row0[grp] + (size_t)t;
+          float* o = p.dgi + row * (3 * H) + k;
+          o[0] = dar; o[H] = daz; o[2 * H] = dan;
+          p.dq[row * H + k] = dqv;
+        }
+      } else {
+        float* so = sgw + (grp * G + ob) * SSEQ + kl;
+        so[0] = dar; so[HU] = daz; so[2 * HU] = dan; so[3 * HU] = dqv;
+      }
+    }
+    if (DIO) {
+#pragma unroll
+      for (int g = 0; g < NGRP; ++g) cur[g] = nxt[g];
     }
   }
-  __syncthreads();
-  store(0, T - 1);
-  cp_async_wait<0>();
+  if (!DIO) {
+    __syncthreads();
+    store(0, T - 1);
+    cp_async_wait<0>();
+  }
   cluster_sync_all();
 }
 
@@ -883,10 +943,10 @@ int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
   return tg_check_launch("gru_cl_fwd");
 }
 
-template <int H, int CS, int NGRP, int PF = CL_PF>
+template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false>
 int launch_cl_bwd(cudaStream_t st, const ClBwdParams& p) {
-  using S = ClBwdSmem<H, CS, NGRP, PF>;
-  auto kern = gru_cl_bwd_kernel<H, CS, NGRP, PF>;
+  using S = ClBwdSmem<H, CS, NGRP, PF, DIO>;
+  auto kern = gru_cl_bwd_kernel<H, CS, NGRP, PF, DIO>;
   TG_OPT_IN_SMEM(kern, "gru_cl_bwd");
   const int clusters = (p.B + S::BT - 1) / S::BT;
   kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
@@ -1009,6 +1069,8 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
                   float* dgi, float* dq, int B, int T, int H, int dy_last) {
   ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
   ClCaps& c = cl_caps();
+  if (H == 128 && tg_cluster_dio())
+    return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, true>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, true>(st, p);
   if (H == 128) return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
   if (H == 256) {
     switch (pick_groups(B, 8, c.b256, 3)) {
