@@ -165,6 +165,18 @@ int tg_cluster_dio() {
   return x;
 }
 
+// output columns per thread in the H = 128 cluster BPTT kernel (2 or 4): TIMEGAN_B200_CLUSTER_NO / tg_set_option("cluster_no", v)
+static std::atomic<int> g_cluster_no{-1};
+int tg_cluster_no() {
+  int x = g_cluster_no.load(std::memory_order_relaxed);
+  if (x < 0) {
+    const char* e = getenv("TIMEGAN_B200_CLUSTER_NO");
+    x = (e && atoi(e) == 2) ? 2 : 4;
+    g_cluster_no.store(x);
+  }
+  return x;
+}
+
 // two-columns-per-thread BPTT kernel for one-sequence-per-CTA launches at H <= 64 (gru_bwd.cu): OFF by default -- it
 // halves the shared-memory operand fetches (12 instead of 24 LDS.128 per step) but pays a second shuffle round on the
 // per-step dependency chain, and measured 283 vs 275 us at the c2 layer shape (profiles/r02_probe_bwd_pair.log).
@@ -206,6 +218,7 @@ int tg_device_sm_count(void) { return tg_num_sms(); }
 int tg_set_option(const char* key, int value) {
   if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
   if (key && strcmp(key, "bwd_pair") == 0) { g_bwd_pair.store(value ? 1 : 0); return TG_OK; }
+  if (key && strcmp(key, "cluster_no") == 0) { g_cluster_no.store(value == 2 ? 2 : 4); return TG_OK; }
   if (key && strcmp(key, "cluster_dio") == 0) { g_cluster_dio.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster_jvp256") == 0) { g_cluster_jvp256.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster") == 0) { g_use_cluster.store(value < 0 || value > 2 ? 1 : value); return TG_OK; }

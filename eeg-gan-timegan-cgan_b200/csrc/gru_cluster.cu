@@ -395,13 +395,16 @@ struct ClBwdSmem {
   static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
 };
 
-template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false>
+// NO = output columns per thread (2 or 4): NO*G lanes share a column group, each holding H/(NO*G) rows of W_hh^T per gate
+// and column, so that one LDS.128 of the dGH vector feeds 2*NO FFMA2 -- NO = 4 halves the operand fetches of the mat-vec
+// again (24 instead of 48 LDS.128 per thread and step at H = 128) for one more shuffle round in the reduction.
+template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false, int NO = 2>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_bwd_kernel(ClBwdParams p) {
   using S = ClBwdSmem<H, CS, NGRP, PF, DIO>;
   constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR;
-  constexpr int L2 = 2 * G;            // lanes per output pair
+  constexpr int L2 = NO * G;           // lanes per output group
   constexpr int J = H / L2;            // j values per lane and gate
-  static_assert(J == 16, "96 weight registers per thread");
+  static_assert(NO * 3 * J == 96 && (NO == 2 || NO == 4) && L2 <= 32, "96 weight registers per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);            // [NGRP][2]
   float* dbuf = reinterpret_cast<float*>(smem_raw + 128);            // [2][BT][3][HR]
@@ -412,7 +415,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   const int T = p.T;
   const int b0 = (blockIdx.x / CS) * BT;
   const int ob = ql % G, oo = ql / G;              // the (sequence-in-group, output-of-the-pair) this lane finishes
-  const int kl = 2 * kp + oo;                      // its output column inside the CTA's slice
+  const int kl = NO * kp + oo;                     // its output column inside the CTA's slice
   const int k = (int)rank * HU + kl;
 
   for (int i = tid; i < S::DBUF + S::RING; i += CL_THREADS) dbuf[i] = 0.f;     // (DIO: RING = 0)
@@ -503,15 +506,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 
   // =============================== compute warps ===============================
   // ---- W_hh^T slices: wt[o][g][m] = (W[gH+jj][k0+o], W[gH+jj+1][k0+o]),  jj = (i*L2+ql)*4 + 2*(m&1), i = m>>1 ----
-  float2 wt[2][3][J / 2];
+  float2 wt[NO][3][J / 2];
 #pragma unroll
-  for (int o = 0; o < 2; ++o)
+  for (int o = 0; o < NO; ++o)
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
       for (int i = 0; i < J / 4; ++i) {
         const int jj = (i * L2 + ql) * 4;
-        const int kk = (int)rank * HU + 2 * kp + o;
+        const int kk = (int)rank * HU + NO * kp + o;
         const float a0 = p.whh[(size_t)(g * H + jj + 0) * H + kk], a1 = p.whh[(size_t)(g * H + jj + 1) * H + kk];
         const float a2 = p.whh[(size_t)(g * H + jj + 2) * H + kk], a3 = p.whh[(size_t)(g * H + jj + 3) * H + kk];
         wt[o][g][2 * i] = make_float2(a0, a1);
@@ -522,11 +525,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   // Senders: output columns come in runs of four consecutive kl = 2*kp + oo; the run of lane (kp, oo, ob) lives in the
   // lanes ((kr + i) >> 1) * L2 + ((kr + i) & 1) * G + ob of the same warp (kr = first column of the run in the warp)
   const int lane = tid & 31;
-  const int wbase = lane - (kp % (32 / L2)) * L2 - oo * G;          // lane of (first pair of the warp, oo = 0, same ob)
-  const int kr = (kl & ~3) - 2 * (kp - kp % (32 / L2));            // first column of the run, relative to the warp's
+  const int kr = (kl & ~3) - NO * (kp - kp % (32 / L2));           // first column of the run, relative to the warp's
   int srcl[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) srcl[i] = wbase + ((kr + i) >> 1) * L2 + ((kr + i) & 1) * G;
+  for (int i = 0; i < 4; ++i) srcl[i] = ((kr + i) / NO) * L2 + ((kr + i) % NO) * G + ob;
+  (void)lane;
   // lane i of the run (kl & 3) serves the destination CTAs c == i (mod 4): one warp instruction covers four CTAs
   constexpr int ND = (CS + 3) / 4;
   uint32_t r_d[ND], r_bar[ND];
@@ -578,9 +581,11 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
       if (s > 0) {
         mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((s - 1) >> 1) & 1));
         if (tid == 0 && s + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);
-        float2 acc[G][2];
+        float2 acc[G][NO];
 #pragma unroll
-        for (int b = 0; b < G; ++b) acc[b][0] = acc[b][1] = make_float2(0.f, 0.f);
+        for (int b = 0; b < G; ++b)
+#pragma unroll
+          for (int o = 0; o < NO; ++o) acc[b][o] = make_float2(0.f, 0.f);
         const uint32_t dc = dbuf_a + (uint32_t)((ppar * BT + grp * G) * 3 * HR) * 4u + 16u * (uint32_t)ql;
         // operand fetches run one (row block, gate) ahead of the FFMA2s that consume them
         float4 dvv[2][G];
@@ -604,7 +609,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
             const float4 dv = dvv[it & 1][b];
             const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
 #pragma unroll
-            for (int o = 0; o < 2; ++o) {
+            for (int o = 0; o < NO; ++o) {
               acc[b][o] = __ffma2_rn(wt[o][g][2 * i], d01, acc[b][o]);
               acc[b][o] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[b][o]);
             }
@@ -612,7 +617,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         }
         float v[L2];
 #pragma unroll
-        for (int o = 0; o < 2; ++o)
+        for (int o = 0; o < NO; ++o)
 #pragma unroll
           for (int b = 0; b < G; ++b) v[o * G + b] = acc[b][o].x + acc[b][o].y;
         reduce_scatter<L2>(v, ql);
@@ -702,12 +707,12 @@ struct ClJbSmem {
   static constexpr size_t bytes = (size_t)(DBUF + RING + STG) * 4 + 128;
 };
 
-template <int H, int CS, int NGRP>
+template <int H, int CS, int NGRP, int NO = 2>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_jvp_bwd_kernel(ClJbParams p) {
   using S = ClJbSmem<H, CS, NGRP>;
   constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR;
-  constexpr int L2 = 2 * G, J = H / L2;
-  static_assert(J == 16, "96 weight registers per thread");
+  constexpr int L2 = NO * G, J = H / L2;       // NO output columns per thread (see gru_cl_bwd_kernel)
+  static_assert(NO * 3 * J == 96 && (NO == 2 || NO == 4) && L2 <= 32, "96 weight registers per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   float* dbuf = reinterpret_cast<float*>(smem_raw + 128);            // [2][BT][6][HR]
@@ -718,7 +723,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   const int T = p.T;
   const int b0 = (blockIdx.x / CS) * BT;
   const int ob = ql % G, oo = ql / G;
-  const int kl = 2 * kp + oo;
+  const int kl = NO * kp + oo;
   const int k = (int)rank * HU + kl;
 
   for (int i = tid; i < S::DBUF + S::RING; i += CL_THREADS) dbuf[i] = 0.f;
@@ -785,15 +790,15 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   };
   for (int s = 0; s < CL_PF - 1; ++s) prefetch(T - 1 - s);
 
-  float2 wt[2][3][J / 2];
+  float2 wt[NO][3][J / 2];
 #pragma unroll
-  for (int o = 0; o < 2; ++o)
+  for (int o = 0; o < NO; ++o)
 #pragma unroll
     for (int g = 0; g < 3; ++g)
 #pragma unroll
       for (int i = 0; i < J / 4; ++i) {
         const int jj = (i * L2 + ql) * 4;
-        const int kk = (int)rank * HU + 2 * kp + o;
+        const int kk = (int)rank * HU + NO * kp + o;
         const float a0 = p.whh[(size_t)(g * H + jj + 0) * H + kk], a1 = p.whh[(size_t)(g * H + jj + 1) * H + kk];
         const float a2 = p.whh[(size_t)(g * H + jj + 2) * H + kk], a3 = p.whh[(size_t)(g * H + jj + 3) * H + kk];
         wt[o][g][2 * i] = make_float2(a0, a1);
@@ -801,12 +806,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
       }
   cluster_sync_all();
 
-  const int lane = tid & 31;
-  const int wbase = lane - (kp % (32 / L2)) * L2 - oo * G;
-  const int kr = (kl & ~3) - 2 * (kp - kp % (32 / L2));
+  const int kr = (kl & ~3) - NO * (kp - kp % (32 / L2));
   int srcl[4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) srcl[i] = wbase + ((kr + i) >> 1) * L2 + ((kr + i) & 1) * G;
+  for (int i = 0; i < 4; ++i) srcl[i] = ((kr + i) / NO) * L2 + ((kr + i) % NO) * G + ob;
   constexpr int ND = (CS + 3) / 4;
   uint32_t r_d[ND], r_bar[ND];
   bool r_ok[ND];
@@ -857,11 +860,13 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
       if (s > 0) {
         mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((s - 1) >> 1) & 1));
         if (tid == 0 && s + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);
-        float2 acc[G][2][2];          // [sequence][adjoint][output column]
+        float2 acc[G][2][NO];         // [sequence][adjoint][output column]
 #pragma unroll
         for (int b = 0; b < G; ++b)
 #pragma unroll
-          for (int v = 0; v < 2; ++v) acc[b][v][0] = acc[b][v][1] = make_float2(0.f, 0.f);
+          for (int v = 0; v < 2; ++v)
+#pragma unroll
+            for (int o = 0; o < NO; ++o) acc[b][v][o] = make_float2(0.f, 0.f);
         const uint32_t dc = dbuf_a + (uint32_t)((ppar * BT + grp * G) * 6 * HR) * 4u + 16u * (uint32_t)ql;
 #pragma unroll
         for (int i = 0; i < J / 4; ++i)
@@ -874,7 +879,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
                 const float4 dv = lds_v4(dc + (uint32_t)((b * 6 + v * 3 + g) * HR) * 4u + (uint32_t)(i * L2) * 16u);
                 const float2 d01 = make_float2(dv.x, dv.y), d23 = make_float2(dv.z, dv.w);
 #pragma unroll
-                for (int o = 0; o < 2; ++o) {
+                for (int o = 0; o < NO; ++o) {
                   acc[b][v][o] = __ffma2_rn(wt[o][g][2 * i], d01, acc[b][v][o]);
                   acc[b][v][o] = __ffma2_rn(wt[o][g][2 * i + 1], d23, acc[b][v][o]);
                 }
@@ -883,7 +888,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         for (int v = 0; v < 2; ++v) {
           float u[L2];
 #pragma unroll
-          for (int o = 0; o < 2; ++o)
+          for (int o = 0; o < NO; ++o)
 #pragma unroll
             for (int b = 0; b < G; ++b) u[o * G + b] = acc[b][v][o].x + acc[b][v][o].y;
           reduce_scatter<L2>(u, ql);
@@ -923,10 +928,10 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
   cluster_sync_all();
 }
 
-template <int H, int CS, int NGRP>
+template <int H, int CS, int NGRP, int NO = 2>
 int launch_cl_jb(cudaStream_t st, const ClJbParams& p) {
   using S = ClJbSmem<H, CS, NGRP>;
-  auto kern = gru_cl_jvp_bwd_kernel<H, CS, NGRP>;
+  auto kern = gru_cl_jvp_bwd_kernel<H, CS, NGRP, NO>;
   TG_OPT_IN_SMEM(kern, "gru_cl_jvp_bwd");
   const int clusters = (p.B + S::BT - 1) / S::BT;
   kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
@@ -943,10 +948,10 @@ int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
   return tg_check_launch("gru_cl_fwd");
 }
 
-template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false>
+template <int H, int CS, int NGRP, int PF = CL_PF, bool DIO = false, int NO = 2>
 int launch_cl_bwd(cudaStream_t st, const ClBwdParams& p) {
   using S = ClBwdSmem<H, CS, NGRP, PF, DIO>;
-  auto kern = gru_cl_bwd_kernel<H, CS, NGRP, PF, DIO>;
+  auto kern = gru_cl_bwd_kernel<H, CS, NGRP, PF, DIO, NO>;
   TG_OPT_IN_SMEM(kern, "gru_cl_bwd");
   const int clusters = (p.B + S::BT - 1) / S::BT;
   kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
@@ -1069,9 +1074,18 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
                   float* dgi, float* dq, int B, int T, int H, int dy_last) {
   ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
   ClCaps& c = cl_caps();
+  if (H == 128 && tg_cluster_no() == 4)
+    return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, false, 4>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, false, 4>(st, p);
   if (H == 128 && tg_cluster_dio())
     return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, true>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, true>(st, p);
   if (H == 128) return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
+  if (H == 256 && tg_cluster_no() == 4) {
+    switch (pick_groups(B, 8, c.b256, 3)) {
+      case 1: return launch_cl_bwd<256, 8, 1, CL_PF, false, 4>(st, p);
+      case 2: return launch_cl_bwd<256, 8, 2, CL_PF, false, 4>(st, p);
+      default: return launch_cl_bwd<256, 8, 3, 2, false, 4>(st, p);
+    }
+  }
   if (H == 256) {
     switch (pick_groups(B, 8, c.b256, 3)) {
       case 1: return launch_cl_bwd<256, 8, 1>(st, p);
@@ -1100,8 +1114,10 @@ int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, co
                       const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh, float* gib,
                       float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only) {
   ClJbParams p{hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, last_only};
+  if (H == 128 && tg_cluster_no() == 4)
+    return pick_groups(B, 4, cl_caps().j128, 2) == 1 ? launch_cl_jb<128, 2, 1, 4>(st, p) : launch_cl_jb<128, 2, 2, 4>(st, p);
   if (H == 128) return pick_groups(B, 4, cl_caps().j128, 2) == 1 ? launch_cl_jb<128, 2, 1>(st, p) : launch_cl_jb<128, 2, 2>(st, p);
-  if (H == 256) return launch_cl_jb<256, 8, 1>(st, p);
+  if (H == 256) return tg_cluster_no() == 4 ? launch_cl_jb<256, 8, 1, 4>(st, p) : launch_cl_jb<256, 8, 1>(st, p);
   tg_set_error("gru_cl_jvp_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }

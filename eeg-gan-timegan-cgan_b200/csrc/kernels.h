@@ -40,6 +40,7 @@ bool tg_cluster_takes(int H, int B, bool backward);
 int tg_use_cluster();
 int tg_cluster_jvp256();
 int tg_cluster_dio();
+int tg_cluster_no();
 int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh, float* y, float* q, int B, int T, int H,
                   int save);
 int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const float* q, const float* y, const float* whh,
