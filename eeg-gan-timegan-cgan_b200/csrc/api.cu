@@ -171,7 +171,7 @@ int tg_cluster_no() {
   int x = g_cluster_no.load(std::memory_order_relaxed);
   if (x < 0) {
     const char* e = getenv("TIMEGAN_B200_CLUSTER_NO");
-    x = (e && atoi(e) == 2) ? 2 : 4;
+    x = (e && (atoi(e) == 2 || atoi(e) == 8)) ? atoi(e) : 4;     // 8: also two hidden units per thread in the H = 128 forward
     g_cluster_no.store(x);
   }
   return x;
@@ -218,7 +218,7 @@ int tg_device_sm_count(void) { return tg_num_sms(); }
 int tg_set_option(const char* key, int value) {
   if (key && strcmp(key, "wgrad_ctas") == 0) { g_wgrad_cta_cap.store(value < 0 ? 0 : value); return TG_OK; }
   if (key && strcmp(key, "bwd_pair") == 0) { g_bwd_pair.store(value ? 1 : 0); return TG_OK; }
-  if (key && strcmp(key, "cluster_no") == 0) { g_cluster_no.store(value == 2 ? 2 : 4); return TG_OK; }
+  if (key && strcmp(key, "cluster_no") == 0) { g_cluster_no.store((value == 2 || value == 8) ? value : 4); return TG_OK; }
   if (key && strcmp(key, "cluster_dio") == 0) { g_cluster_dio.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster_jvp256") == 0) { g_cluster_jvp256.store(value ? 1 : 0); return TG_OK; }
   if (key && strcmp(key, "cluster") == 0) { g_use_cluster.store(value < 0 || value > 2 ? 1 : value); return TG_OK; }

@@ -153,17 +153,22 @@ struct ClFwdSmem {
   static constexpr size_t bytes = (size_t)(HBUF + RING + STG) * 4 + 128;
 };
 
-template <int H, int CS, int NGRP, int SG>
+// NH = hidden units per thread in the mat-vec (1 or 2): with NH = 2 the NH*G lanes of a unit pair each hold H/(NH*G) columns
+// of both units' gate rows, so one LDS.128 of h feeds 12 FFMA2 instead of 6 (half the operand fetches); the partial sums of
+// 2 units x G sequences are reduce-scattered over the 2G lanes, which leaves every lane with the totals of the SAME (unit,
+// sequence) it owns with NH = 1 -- gates, all-gather and staging are unchanged.
+template <int H, int CS, int NGRP, int SG, int NH = 1>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_cl_fwd_kernel(ClFwdParams p) {
   using S = ClFwdSmem<H, CS, NGRP, SG>;
-  constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR, KS = H / G;
-  static_assert(KS == 32, "96 weight registers per thread");
+  constexpr int HU = S::HU, G = S::G, BT = S::BT, HR = S::HR, L2 = NH * G, KS = H / L2;
+  static_assert(NH * 3 * KS == 96 && (NH == 1 || (NH == 2 && SG == G)), "96 weight registers per thread");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);            // [NGRP][2]
   float* hbuf = reinterpret_cast<float*>(smem_raw + 128);            // [2][BT][HR]
   float* ring = hbuf + S::HBUF;                                      // [PF][BT][3][HU]
   float* stg = ring + S::RING;                                       // [2][BT][5][HU]
   const int tid = threadIdx.x, jl = tid / G, ql = tid % G;
+  const int qk = tid % L2, uo = qk / G;            // k-slice lane inside the unit group; which unit of the group this lane owns
   const uint32_t rank = cluster_ctarank();
   const int j = (int)rank * HU + jl;
   const int T = p.T;
@@ -224,17 +229,19 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
 
   // =============================== compute warps ===============================
   // ---- W_hh slice into registers (float2 pairs for FFMA2) ----
-  float2 w[3][KS / 2];
+  float2 w[NH][3][KS / 2];
   float bh[3];
 #pragma unroll
   for (int g = 0; g < 3; ++g) {
     bh[g] = p.bhh[g * H + j];
 #pragma unroll
-    for (int i = 0; i < KS / 4; ++i) {
-      const float4 v = *reinterpret_cast<const float4*>(p.whh + (size_t)(g * H + j) * H + (i * G + ql) * 4);
-      w[g][2 * i] = make_float2(v.x, v.y);
-      w[g][2 * i + 1] = make_float2(v.z, v.w);
-    }
+    for (int u = 0; u < NH; ++u)
+#pragma unroll
+      for (int i = 0; i < KS / 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(p.whh + (size_t)(g * H + j - uo + u) * H + (i * L2 + qk) * 4);
+        w[u][g][2 * i] = make_float2(v.x, v.y);
+        w[u][g][2 * i + 1] = make_float2(v.z, v.w);
+      }
   }
   cluster_sync_all();      // every CTA's barriers are initialised and armed before anybody sends
 
@@ -275,16 +282,19 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     float* sgw = stg + par * (BT * SSEQ);
     const float* ringt = ring + (t % CL_PF) * (BT * RSEQ);
     // everything after a group's mat-vec: combine the lane partials, gates, state update, all-gather, staging
-    auto post = [&](const int grp, float2 (&acc)[SG][3]) __attribute__((always_inline)) {
+    auto post = [&](const int grp, float2 (&acc)[NH][SG][3]) __attribute__((always_inline)) {
       const float* gr_ = ringt + (grp * SG + ob) * RSEQ + jl;
       const float gr = gr_[0], gz = gr_[HU], gn = gr_[2 * HU];
       float own[3];
 #pragma unroll
       for (int g = 0; g < 3; ++g) {
-        float v[SG];
+        float v[NH * SG];
 #pragma unroll
-        for (int b = 0; b < SG; ++b) v[b] = acc[b][g].x + acc[b][g].y;
-        reduce_partial<G, SG>(v, ql);
+        for (int u = 0; u < NH; ++u)
+#pragma unroll
+          for (int b = 0; b < SG; ++b) v[u * SG + b] = acc[u][b][g].x + acc[u][b][g].y;
+        if constexpr (NH == 1) reduce_partial<G, SG>(v, ql);
+        else reduce_scatter<L2>(v, qk);
         own[g] = v[0];
       }
       const float r = sigmoid_mufu(gr + own[0]);
@@ -311,7 +321,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
     // block as group g+1's mat-vec so that the scheduler may interleave them.  Half-size groups (SG = G/2, twice as many
     // of them) were tried to hide the chain at B <= 296 too: 2267 vs 2006 clk/step at H = 128 -- the duplicated gate work
     // and the second barrier wait cost more than the overlap gains -- so the launcher uses SG = G.
-    float2 accs[2][SG][3];
+    float2 accs[2][NH][SG][3];
 #pragma unroll
     for (int grp = 0; grp < NGRP; ++grp) {
       // ---- wait for h_{t-1} of this group (all CTAs' slices) ----
@@ -319,14 +329,17 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         mbar_wait_susp(&bars[grp * 2 + ppar], (uint32_t)(((t - 1) >> 1) & 1));
         if (tid == 0 && t + 1 < T) mbar_expect_tx(&bars[grp * 2 + ppar], TXB);   // re-arm for step t+1's values
       }
-      float2 (&acc)[SG][3] = accs[grp & 1];
+      float2 (&acc)[NH][SG][3] = accs[grp & 1];
 #pragma unroll
-      for (int b = 0; b < SG; ++b) {
-        acc[b][0] = make_float2((b == ql) ? bh[0] : 0.f, 0.f);
-        acc[b][1] = make_float2((b == ql) ? bh[1] : 0.f, 0.f);
-        acc[b][2] = make_float2(0.f, 0.f);
-      }
-      const uint32_t hc = hbuf_a + (uint32_t)((ppar * BT + grp * SG) * HR) * 4u + 16u * (uint32_t)ql;
+      for (int u = 0; u < NH; ++u)
+#pragma unroll
+        for (int b = 0; b < SG; ++b) {
+          const bool mine = (b == ql) && (u == uo);       // the lane that owns (unit, sequence) seeds its hidden biases
+          acc[u][b][0] = make_float2(mine ? bh[0] : 0.f, 0.f);
+          acc[u][b][1] = make_float2(mine ? bh[1] : 0.f, 0.f);
+          acc[u][b][2] = make_float2(0.f, 0.f);
+        }
+      const uint32_t hc = hbuf_a + (uint32_t)((ppar * BT + grp * SG) * HR) * 4u + 16u * (uint32_t)qk;
       // operand fetches run one k-block ahead of the FFMA2s that consume them (two warps per scheduler cannot hide the
       // shared-memory latency by themselves: short-scoreboard was the top stall of the mat-vec)
       float4 hv[2][SG];
@@ -337,7 +350,7 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         if (i + 1 < KS / 4) {
 #pragma unroll
           for (int b = 0; b < SG; ++b)
-            hv[(i + 1) & 1][b] = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)((i + 1) * G) * 16u);
+            hv[(i + 1) & 1][b] = lds_v4(hc + (uint32_t)(b * HR) * 4u + (uint32_t)((i + 1) * L2) * 16u);
         }
         if (CL_IO_IN_MATVEC && grp == 0 && i == 1) {
           if (t > 0) store(t - 1);
@@ -347,10 +360,12 @@ __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(CL_THREADS, 1) gru_
         for (int b = 0; b < SG; ++b) {
           const float2 h01 = make_float2(hv[i & 1][b].x, hv[i & 1][b].y), h23 = make_float2(hv[i & 1][b].z, hv[i & 1][b].w);
 #pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            acc[b][g] = __ffma2_rn(w[g][2 * i], h01, acc[b][g]);
-            acc[b][g] = __ffma2_rn(w[g][2 * i + 1], h23, acc[b][g]);
-          }
+          for (int u = 0; u < NH; ++u)
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+              acc[u][b][g] = __ffma2_rn(w[u][g][2 * i], h01, acc[u][b][g]);
+              acc[u][b][g] = __ffma2_rn(w[u][g][2 * i + 1], h23, acc[u][b][g]);
+            }
         }
       }
       if (grp > 0) post(grp - 1, accs[(grp - 1) & 1]);
@@ -938,10 +953,10 @@ int launch_cl_jb(cudaStream_t st, const ClJbParams& p) {
   return tg_check_launch("gru_cl_jvp_bwd");
 }
 
-template <int H, int CS, int NGRP, int SG>
+template <int H, int CS, int NGRP, int SG, int NH = 1>
 int launch_cl_fwd(cudaStream_t st, const ClFwdParams& p) {
   using S = ClFwdSmem<H, CS, NGRP, SG>;
-  auto kern = gru_cl_fwd_kernel<H, CS, NGRP, SG>;
+  auto kern = gru_cl_fwd_kernel<H, CS, NGRP, SG, NH>;
   TG_OPT_IN_SMEM(kern, "gru_cl_fwd");
   const int clusters = (p.B + S::BT - 1) / S::BT;
   kern<<<clusters * CS, CL_THREADS, S::bytes, st>>>(p);
@@ -1057,6 +1072,10 @@ int tg_gru_cl_fwd(cudaStream_t st, float* gi, const float* whh, const float* bhh
                   int save) {
   ClFwdParams p{gi, whh, bhh, y, q, B, T, save};
   ClCaps& c = cl_caps();
+  // two hidden units per thread (NH = 2) halves the forward's operand fetches too, but the forward was never bound by them
+  // (it reads one h vector for three gates): 745 vs 759 us at B = 256, 1380 vs 1367 us at B = 512 -- NH = 1 stays
+  if (H == 128 && tg_cluster_no() == 8)
+    return pick_groups(B, 4, c.f128, 2) == 1 ? launch_cl_fwd<128, 2, 1, 4, 2>(st, p) : launch_cl_fwd<128, 2, 2, 4, 2>(st, p);
   if (H == 128) return pick_groups(B, 4, c.f128, 2) == 1 ? launch_cl_fwd<128, 2, 1, 4>(st, p) : launch_cl_fwd<128, 2, 2, 4>(st, p);
   if (H == 256) {
     switch (pick_groups(B, 8, c.f256, 4)) {
@@ -1074,12 +1093,12 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
                   float* dgi, float* dq, int B, int T, int H, int dy_last) {
   ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
   ClCaps& c = cl_caps();
-  if (H == 128 && tg_cluster_no() == 4)
+  if (H == 128 && tg_cluster_no() >= 4)
     return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, false, 4>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, false, 4>(st, p);
   if (H == 128 && tg_cluster_dio())
     return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, true>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, true>(st, p);
   if (H == 128) return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1>(st, p) : launch_cl_bwd<128, 2, 2>(st, p);
-  if (H == 256 && tg_cluster_no() == 4) {
+  if (H == 256 && tg_cluster_no() >= 4) {
     switch (pick_groups(B, 8, c.b256, 3)) {
       case 1: return launch_cl_bwd<256, 8, 1, CL_PF, false, 4>(st, p);
       case 2: return launch_cl_bwd<256, 8, 2, CL_PF, false, 4>(st, p);
@@ -1114,10 +1133,10 @@ int tg_gru_cl_jvp_bwd(cudaStream_t st, const float* hbar, const float* hdbar, co
                       const float* ta, const float* qdot, const float* y, const float* ydot, const float* whh, float* gib,
                       float* qb, float* gidb, float* qdb, int B, int T, int H, int last_only) {
   ClJbParams p{hbar, hdbar, rzn, q, ta, qdot, y, ydot, whh, gib, qb, gidb, qdb, B, T, last_only};
-  if (H == 128 && tg_cluster_no() == 4)
+  if (H == 128 && tg_cluster_no() >= 4)
     return pick_groups(B, 4, cl_caps().j128, 2) == 1 ? launch_cl_jb<128, 2, 1, 4>(st, p) : launch_cl_jb<128, 2, 2, 4>(st, p);
   if (H == 128) return pick_groups(B, 4, cl_caps().j128, 2) == 1 ? launch_cl_jb<128, 2, 1>(st, p) : launch_cl_jb<128, 2, 2>(st, p);
-  if (H == 256) return tg_cluster_no() == 4 ? launch_cl_jb<256, 8, 1, 4>(st, p) : launch_cl_jb<256, 8, 1>(st, p);
+  if (H == 256) return tg_cluster_no() >= 4 ? launch_cl_jb<256, 8, 1, 4>(st, p) : launch_cl_jb<256, 8, 1>(st, p);
   tg_set_error("gru_cl_jvp_bwd: hidden size %d not supported", H);
   return TG_ERR_UNSUPPORTED;
 }
