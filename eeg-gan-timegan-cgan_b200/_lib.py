@@ -40,7 +40,7 @@ SIGNATURES = {
     "tg_prof_reset": (None, []),
     "tg_prof_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_ll), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "tg_proj": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i]),
-    "tg_bf16_gi_supported": (_i, [_i, _i, _i]),
+    "tg_bf16_gi_supported": (_i, [_i, _i, _i, _i]),
     "tg_proj_bf16": (_i, [_vp, _vp, _i, _vp, _i, _vp, _vp, _i, _i, _i, _i]),
     "tg_dgrad": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i]),
     "tg_wgrad_workspace_bytes": (_sz, [_i, _i, _i]),

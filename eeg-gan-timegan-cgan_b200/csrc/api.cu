@@ -270,7 +270,11 @@ int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, cons
   return tg_gemm_nt_impl((cudaStream_t)stream, A, lda, W, ldw, bias, C, ldc, M, N, K, accumulate);
 }
 
-int tg_bf16_gi_supported(int M, int K, int H) {
+int tg_bf16_gi_supported(int B, int T, int K, int H) {
+  const long long M = (long long)B * T;
+  // a batch that the cluster forward kernel takes (H = 128, more sequences than one-SM CTAs fit: the discriminator's 2B pass)
+  // keeps the fp32-gi path: that kernel has no bf16-input variant and is the faster one there (1367 vs 1557 us at B = 512)
+  if (tg_cluster_takes(H, B, false)) return 0;
   return (tg_gru_fwd_bf16gi_ok(H) && M >= 128 && K % 4 == 0 && K <= 512) ? 1 : 0;
 }
 

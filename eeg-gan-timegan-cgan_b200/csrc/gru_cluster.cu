@@ -1093,6 +1093,8 @@ int tg_gru_cl_bwd(cudaStream_t st, const float* dy, const float* rzn, const floa
                   float* dgi, float* dq, int B, int T, int H, int dy_last) {
   ClBwdParams p{dy, rzn, q, y, whh, dgi, dq, B, T, dy_last};
   ClCaps& c = cl_caps();
+  if (H == 128 && tg_cluster_no() >= 4 && tg_cluster_dio())
+    return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, true, 4>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, true, 4>(st, p);
   if (H == 128 && tg_cluster_no() >= 4)
     return pick_groups(B, 4, c.b128, 2) == 1 ? launch_cl_bwd<128, 2, 1, CL_PF, false, 4>(st, p) : launch_cl_bwd<128, 2, 2, CL_PF, false, 4>(st, p);
   if (H == 128 && tg_cluster_dio())

@@ -260,7 +260,7 @@ def stack_forward(x: torch.Tensor, weights: Sequence[torch.Tensor], save: bool,
         y = torch.empty(B, T, H, dtype=torch.float32, device=x.device)
         q = torch.empty(B, T, H, dtype=torch.float32, device=x.device) if save else None
         K = inp.shape[-1]
-        if _BF16_GI and lib.tg_bf16_gi_supported(B * T, K, H):
+        if _BF16_GI and lib.tg_bf16_gi_supported(B, T, K, H):
             # bf16 input projection: bf16 operands, bf16 gi (half the bytes of the layer's largest tensor, out of the
             # projection and into the recurrence); r,z,n are saved in fp32 in their own tensor
             gi16 = torch.empty(B, T, 3 * H, dtype=torch.bfloat16, device=x.device)

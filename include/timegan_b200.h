@@ -75,8 +75,9 @@ int tg_proj(void* stream, const float* A, int lda, const float* W, int ldw, cons
  * A (M,K) fp32 is converted to bf16 inside the kernel (no bf16 copy of an activation is written to memory), W16 (N,K) is
  * bf16, the MMA is tcgen05 kind::f16 with fp32 accumulation, the result C16 (M,N) is bf16: 2 bytes per gate
  * pre-activation out of the projection and into tg_gru_fwd_bf16gi.  lda in floats, ldw / ldc in bf16 elements.
- * tg_bf16_gi_supported: 1 when both kernels take this layer (M = B*T rows, K inputs, hidden size H: H = 64 or 128). */
-int tg_bf16_gi_supported(int M, int K, int H);
+ * tg_bf16_gi_supported: 1 when both kernels take this layer (B sequences of T steps, K inputs, hidden size H: H = 64 or
+ * 128, and not a batch for which the cluster forward kernel -- fp32 gi only -- is the faster recurrence). */
+int tg_bf16_gi_supported(int B, int T, int K, int H);
 int tg_proj_bf16(void* stream, const float* A, int lda, const void* W16, int ldw, const float* bias, void* C16, int ldc,
                  int M, int N, int K);
 

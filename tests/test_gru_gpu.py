@@ -346,8 +346,9 @@ def test_forward_from_bf16_gi_is_the_fp32_kernel_on_the_widened_input(B, T, H, b
 
 def test_bf16_gi_unsupported_hidden_size_is_refused():
     from timegan_b200._lib import lib, ptr, stream_ptr
-    assert lib.tg_bf16_gi_supported(4096, 64, 64) == 1 and lib.tg_bf16_gi_supported(4096, 128, 128) == 1
-    assert lib.tg_bf16_gi_supported(4096, 24, 24) == 0 and lib.tg_bf16_gi_supported(64, 64, 64) == 0
+    assert lib.tg_bf16_gi_supported(8, 512, 64, 64) == 1 and lib.tg_bf16_gi_supported(8, 512, 128, 128) == 1
+    assert lib.tg_bf16_gi_supported(8, 512, 24, 24) == 0 and lib.tg_bf16_gi_supported(2, 32, 64, 64) == 0
+    assert lib.tg_bf16_gi_supported(512, 768, 128, 128) == 0     # the cluster forward kernel's batch: fp32 gi
     t = torch.zeros(2, 4, 72, device="cuda:0")
     rc = lib.tg_gru_fwd_bf16gi(stream_ptr(), ptr(t), ptr(t), ptr(t), ptr(t), None, None, 2, 4, 24, 0)
     assert rc == -4
